@@ -1,0 +1,171 @@
+/* npswf.h — C ABI of the B200-native NPS waveform path (libnpswf.so).
+ *
+ * Drop-in boundary for the per-event, per-block hot path of the reference macro
+ * (/root/reference/TEST_2.C, the npsWF.C lineage; "T2:N" = line N of that file).  The
+ * reference has no FFI: its stages are free functions / lambdas in one ROOT macro, called once
+ * per event by RDataFrame (T2:1305).  This library replaces the `Define("tuple", analyze, ...)`
+ * step for a BATCH of events; each entry point cites the reference interface it replaces.
+ *
+ * Conventions: plain pointers and sizes only; caller owns every host buffer; return 0 = ok,
+ * < 0 = error (message via npswf_last_error); nothing throws across the boundary; a handle is
+ * used by one host thread at a time; host-buffer calls are synchronous w.r.t. their outputs.
+ * There is NO CPU fallback: every compute entry point fails with NPSWF_ERR_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef NPSWF_H
+#define NPSWF_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* shape of the detector / waveform, fixed at compile time as in T2:51-73 */
+#define NPSWF_NTIME 110       /* ntime        T2:51 */
+#define NPSWF_NCOL 30         /* ncol         T2:54 */
+#define NPSWF_NLIN 36         /* nlin         T2:55 */
+#define NPSWF_NBLOCKS 1080    /* nblocks      T2:56 */
+#define NPSWF_MAXWFPULSES 12  /* maxwfpulses  T2:59 */
+#define NPSWF_MFWIDTH 11      /* mfwidth      T2:67 */
+
+enum {
+    NPSWF_OK = 0,
+    NPSWF_ERR_ARG = -1,
+    NPSWF_ERR_CUDA = -2,   /* no usable device / CUDA runtime error */
+    NPSWF_ERR_NOMEM = -3,
+    NPSWF_ERR_CALIB = -4
+};
+
+/* status bits per (event, block) */
+enum {
+    NPSWF_ST_PRESENT = 1,   /* pres==1 && preswf==1                     T2:944 */
+    NPSWF_ST_OKTOFIT = 2,   /* PassClusterThreshold returned true       T2:962 */
+    NPSWF_ST_FIT_OK1 = 4,   /* first fit attempt converged              T2:755 */
+    NPSWF_ST_FIT_OK2 = 8,   /* retry (tougher configuration) converged  T2:761-768 */
+    NPSWF_ST_FALLBACK = 16  /* both failed: TSpectrum values, chi2=-100 T2:774-791 */
+};
+
+/* The tunables of T2:64-73, 81, 354 (compile-time constants in the reference). */
+typedef struct NpsWfConfig {
+    double specthres;    /* 0.02  T2:70  TSpectrum::Search threshold                     */
+    double mfthres;      /* 1.5   T2:71  matched-filter amplitude cut (mV)               */
+    double trig_thres;   /* 10    T2:72  3x3 sum threshold (mV)                          */
+    int32_t coinc_width; /* 20    T2:73  half-width of the coincidence window (bins)     */
+    double dt;           /* 4     T2:354 ns per sample                                    */
+    double timerefacc;   /* 0     T2:81, 524 (calodist-9.5)/(3e8*1e-9*4), in bins         */
+    int32_t n_devices;   /* number of GPUs to shard events over (contiguous ranges); 0 = 1 */
+    const int32_t *devices; /* CUDA ordinals [n_devices]; NULL = 0..n_devices-1           */
+    int32_t chunk_events;   /* events per internal device chunk; 0 = default (512)        */
+    int32_t fit_max_iter;   /* LM iterations of the first attempt; 0 = default            */
+    int32_t fit_retry_max_iter; /* LM iterations of the retry; 0 = default                */
+} NpsWfConfig;
+
+/* The calibration globals of T2:74-85 as loaded at T2:360-469.  mfyref / mfint are derived
+ * inside npswf_create exactly as T2:440-451 does. */
+typedef struct NpsWfCalib {
+    const double *interpX;  /* [NBLOCKS][NTIME]  T2:84, 432 */
+    const double *interpY;  /* [NBLOCKS][NTIME]             */
+    const double *timeref;  /* [NBLOCKS]         T2:77, 437 */
+    const float *cortime;   /* [NBLOCKS]         T2:78, 463 (Float_t) */
+    const int32_t *preswf;  /* [NBLOCKS]         T2:79, 452 */
+} NpsWfCalib;
+
+/* Replaces the atomics nFitFailures / nFitSucceeds (T2:61-62, 1436); summed over all calls. */
+typedef struct NpsWfCounters {
+    int64_t n_events, n_block_waveforms, n_present, n_pass_threshold;
+    int64_t n_fit_attempted;   /* "fitted block-waveforms": present, passed threshold, npulse>0 */
+    int64_t n_fit_ok_first, n_fit_ok_retry, n_fallback;
+    int64_t n_pulses, n_peak_buffer_full, n_fit_iterations;
+} NpsWfCounters;
+
+typedef struct npswf_handle npswf_handle;
+
+void npswf_default_config(NpsWfConfig *cfg);
+int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *calib, npswf_handle **out);
+void npswf_destroy(npswf_handle *h);
+const char *npswf_last_error(const npswf_handle *h); /* h may be NULL: error of the last failed create */
+int npswf_get_counters(npswf_handle *h, NpsWfCounters *out);
+int npswf_reset_counters(npswf_handle *h);
+int npswf_device_count(void);
+
+/* Pinned host allocations for the host-buffer entry points (pageable buffers work, slower). */
+void *npswf_host_alloc(size_t bytes);
+void npswf_host_free(void *p);
+
+/* ---- analyze(event) for a batch: replaces T2:540-1300 / the Define at T2:1305 for the hot
+ * path (block loop T2:942-1022).  Inputs are the unpacked per-event arrays the reference
+ * builds at T2:851-889:
+ *   signal [E][NBLOCKS][NTIME] mV, block-major (idx bn*ntime+it, T2:549);  pres [E][NBLOCKS];
+ *   corr_time_HMS [E] (T2:903).  minsignal is recomputed (min over the trace, init 1e6, T2:884).
+ * Outputs (any may be NULL):
+ *   wfnpulse [E][NBLOCKS]; wftime/wfampl [E][NBLOCKS][12] padded with -999 (the reference's
+ *   scratch init, T2:583-584; flatten with npswf_flatten_event to get T2:1294-1295);
+ *   chi2/timewf/amplwf [E][NBLOCKS] (-100 sentinels, T2:559-561); status [E][NBLOCKS].
+ * Events are sharded over the handle's devices in contiguous ranges; no collective. */
+int npswf_analyze_batch(npswf_handle *h, int64_t n_events, const double *signal, const int32_t *pres,
+                        const double *corr_time_HMS, int32_t *wfnpulse, double *wftime, double *wfampl,
+                        double *chi2, double *timewf, double *amplwf, uint8_t *status);
+
+/* Same, with inputs as int16 ADC counts (signal = counts * lsb_mV; exact on the 12-bit lattice
+ * 1000/4096 mV of T2:357).  Quarter of the PCIe bytes. */
+int npswf_analyze_batch_i16(npswf_handle *h, int64_t n_events, const int16_t *counts, double lsb_mV,
+                            const int32_t *pres, const double *corr_time_HMS, int32_t *wfnpulse, double *wftime,
+                            double *wfampl, double *chi2, double *timewf, double *amplwf, uint8_t *status);
+
+/* Same, all pointers DEVICE memory on the handle's device `dev_slot` (index into cfg.devices),
+ * enqueued on `stream` (a cudaStream_t; NULL = the library's own stream) and NOT synchronised. */
+int npswf_analyze_batch_device(npswf_handle *h, int32_t dev_slot, int64_t n_events, const double *d_signal,
+                               const int32_t *d_pres, const double *d_corr_time_HMS, int32_t *d_wfnpulse,
+                               double *d_wftime, double *d_wfampl, double *d_chi2, double *d_timewf,
+                               double *d_amplwf, uint8_t *d_status, void *stream);
+/* Folds the device-side counters of the last npswf_analyze_batch_device calls into the handle
+ * (synchronises the slot's stream). */
+int npswf_sync_device(npswf_handle *h, int32_t dev_slot, void *stream);
+
+/* ---- stage-level batch entry points (host buffers), one per reference function ---- */
+
+/* FindPulsesMF (T2:124-216) for every present block of every event: matched filter, TSpectrum
+ * search, peak filter.  wftime in TSpectrum bin units (half-integers), wfampl = |s[ti]-min|. */
+int npswf_find_pulses_mf_batch(npswf_handle *h, int64_t n_events, const double *signal, const int32_t *pres,
+                               int32_t *wfnpulse, double *wftime, double *wfampl);
+
+/* PassClusterThreshold (T2:218-278) for every block of every event: ok[e][bn] in {0,1}. */
+int npswf_pass_cluster_threshold_batch(npswf_handle *h, int64_t n_events, const double *signal,
+                                       const int32_t *pres, uint8_t *ok);
+
+/* Fitwf (T2:601-828) for every (event, block) with fit_mask != 0: wfnpulse in; wftime/wfampl
+ * in-out ([12] slots per block, TSpectrum seeds in, fitted / fallback values out); chi2, status out. */
+int npswf_fitwf_batch(npswf_handle *h, int64_t n_events, const double *signal, const double *corr_time_HMS,
+                      const uint8_t *fit_mask, const int32_t *wfnpulse, double *wftime, double *wfampl,
+                      double *chi2, uint8_t *status);
+
+/* Matched-filter tap (T2:145-179): mf [E][NBLOCKS][NTIME] float, the TH1F bin contents. */
+int npswf_matched_filter_batch(npswf_handle *h, int64_t n_events, const double *signal, const int32_t *pres,
+                               float *mf);
+
+/* TSpectrum tap for tests: runs the search kernel on caller-supplied float histograms
+ * hist [n][NTIME]; outputs npeaks [n], pos_x [n][12] (fPositionX before Search()'s bin-centre
+ * conversion), smoothed [n][138] (Markov output), decon [n][NTIME] (destVector).  Any output may be NULL. */
+int npswf_tspectrum_debug(npswf_handle *h, int64_t n, const float *hist, int32_t *npeaks, double *pos_x,
+                          double *smoothed, double *decon);
+
+/* Host helpers (no GPU): derived calibration as the device sees it. */
+int npswf_get_mf_calib(const npswf_handle *h, double *mfyref /*[NBLOCKS][11]*/, double *mfint /*[NBLOCKS]*/);
+int npswf_get_spline(const npswf_handle *h, double *coef /*[NBLOCKS][109][4] = y,b,c,d*/);
+/* Device address of that spline table / timeref on dev_slot (for on-device synthetic generators). */
+const double *npswf_device_spline(const npswf_handle *h, int32_t dev_slot);
+const double *npswf_device_timeref(const npswf_handle *h, int32_t dev_slot);
+
+/* Output packing of T2:1289-1296: flattened wfampl/wftime of one event (blocks with pulses only,
+ * in block order) and blockOffset[NBLOCKS+1] (T2:959-961, 1022).  Returns the total pulse count. */
+int64_t npswf_flatten_event(const int32_t *wfnpulse, const double *wftime_padded, const double *wfampl_padded,
+                            double *wftime_flat, double *wfampl_flat, int32_t *block_offset);
+
+/* Bit-exactness tap: the deterministic exp used by the Markov smoothing kernel, evaluated on
+ * the device for n inputs (host buffers). */
+int npswf_debug_exp(npswf_handle *h, int64_t n, const double *x, double *y);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

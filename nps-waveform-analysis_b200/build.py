@@ -1,0 +1,41 @@
+"""Builds libnpswf.so (the C-ABI product library) and the device-side synthetic generator for sm_100a.
+
+nvcc cross-compiles without a GPU; the .so files are git-ignored but travel to the GPU box.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _stale(out, srcs):
+    if not os.path.exists(out):
+        return True
+    t = os.path.getmtime(out)
+    return any(os.path.getmtime(s) > t for s in srcs)
+
+
+def build(force=False, verbose=False):
+    csrc = os.path.join(HERE, "csrc")
+    srcs = [os.path.join(csrc, f) for f in sorted(os.listdir(csrc))] + [os.path.join(ROOT, "include", "npswf.h")]
+    out = os.path.join(HERE, "lib", "libnpswf.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if force or _stale(out, srcs):
+        cmd = [NVCC] + ARCH + COMMON + (["-Xptxas", "-v"] if verbose else []) + \
+              ["-o", out, os.path.join(csrc, "npswf_api.cu")]
+        subprocess.check_call(cmd)
+    syn = os.path.join(ROOT, "synth")
+    sout = os.path.join(syn, "libnpswf_synth_cuda.so")
+    ssrcs = [os.path.join(syn, "synth_cuda.cu"), os.path.join(syn, "npswf_synth.h")]
+    if force or _stale(sout, ssrcs):
+        subprocess.check_call([NVCC] + ARCH + COMMON + ["-o", sout, ssrcs[0]])
+    return out
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

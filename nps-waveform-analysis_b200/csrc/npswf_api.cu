@@ -1,0 +1,857 @@
+// libnpswf.so — C ABI (include/npswf.h) over the sm_100a kernels.  Host side of the drop-in
+// boundary: handle, per-device calibration + workspaces, chunked double-buffered H2D / compute /
+// D2H pipeline, event sharding over devices (contiguous ranges, one host thread per device, no
+// collective).  There is no CPU fallback: compute entry points fail if CUDA fails.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/npswf.h"
+#include "common.cuh"
+#include "kernel_front.cuh"
+#include "kernel_search.cuh"
+#include "kernel_fit.cuh"
+
+using namespace npswf;
+
+namespace {
+
+std::string g_create_error;
+
+struct Workspace {  // per (device, pipeline stage) buffers for up to `cap` events
+    int64_t cap = 0;
+    double *signal = nullptr;
+    int16_t *counts = nullptr;
+    int32_t *pres = nullptr;
+    double *corr = nullptr;
+    float *mf = nullptr;
+    double *minsig = nullptr;
+    uint8_t *flags = nullptr;
+    int32_t *wfnpulse = nullptr;
+    double *wftime = nullptr, *wfampl = nullptr, *chi2 = nullptr, *timewf = nullptr, *amplwf = nullptr;
+    uint8_t *status = nullptr;
+    uint8_t *mask = nullptr;
+    int *fit_count = nullptr;  // [13]
+    int *fit_list = nullptr;   // [13][cap*B]
+    cudaStream_t stream = nullptr;
+    bool io = false;  // has the signal/pres/output staging buffers (host-buffer API) or only scratch
+};
+
+struct DevSlot {
+    int device = 0;
+    int sm_count = 148;
+    DevCalib cal{};
+    std::vector<void *> owned;
+    Workspace ws[2];
+    DeviceCounters *ctr = nullptr;
+    cudaStream_t own_stream = nullptr;
+};
+
+}  // namespace
+
+struct npswf_handle {
+    NpsWfConfig cfg;
+    KParams kp;
+    std::vector<int> devices;
+    std::vector<DevSlot> slots;
+    std::vector<double> mfyref, mfint, spline, timeref;
+    std::string err;
+    NpsWfCounters host_ctr{};
+    int64_t chunk = 592;
+    std::mutex mu;
+};
+
+namespace {
+
+#define CU_TRY(h, expr)                                                                              \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            char _b[512];                                                                            \
+            snprintf(_b, sizeof _b, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            (h)->err = _b;                                                                           \
+            return NPSWF_ERR_CUDA;                                                                   \
+        }                                                                                            \
+    } while (0)
+
+// Natural cubic spline through unit-or-arbitrary knots (the curve GSL's gsl_interp_cspline
+// represents), solved with the Thomas algorithm.  coef[i] = {y_i, b_i, c_i, d_i}.
+void build_spline(const double *x, const double *y, double *coef)
+{
+    const int n = T;
+    std::vector<double> c(n, 0.0), diag(n), rhs(n), upper(n);
+    // interior equations: h_{i-1} c_{i-1} + 2(h_{i-1}+h_i) c_i + h_i c_{i+1} = 3[(y_{i+1}-y_i)/h_i - (y_i-y_{i-1})/h_{i-1}]
+    for (int i = 1; i < n - 1; i++) {
+        const double h0 = x[i] - x[i - 1], h1 = x[i + 1] - x[i];
+        diag[i] = 2.0 * (h0 + h1);
+        upper[i] = h1;
+        rhs[i] = 3.0 * ((y[i + 1] - y[i]) / h1 - (y[i] - y[i - 1]) / h0);
+    }
+    for (int i = 2; i < n - 1; i++) {  // forward elimination (lower = h_{i-1} = upper[i-1])
+        const double m = upper[i - 1] / diag[i - 1];
+        diag[i] -= m * upper[i - 1];
+        rhs[i] -= m * rhs[i - 1];
+    }
+    for (int i = n - 2; i >= 1; i--) c[i] = (rhs[i] - upper[i] * c[i + 1]) / diag[i];
+    for (int i = 0; i < n - 1; i++) {
+        const double h = x[i + 1] - x[i];
+        coef[4 * i + 0] = y[i];
+        coef[4 * i + 1] = (y[i + 1] - y[i]) / h - h * (c[i + 1] + 2.0 * c[i]) / 3.0;
+        coef[4 * i + 2] = c[i];
+        coef[4 * i + 3] = (c[i + 1] - c[i]) / (3.0 * h);
+    }
+}
+
+template <class Tp>
+int dev_alloc(npswf_handle *h, DevSlot &s, Tp **p, size_t count)
+{
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(Tp));
+    if (e != cudaSuccess) {
+        h->err = std::string("cudaMalloc failed: ") + cudaGetErrorString(e);
+        return NPSWF_ERR_NOMEM;
+    }
+    s.owned.push_back(q);
+    *p = reinterpret_cast<Tp *>(q);
+    return 0;
+}
+
+template <class Tp>
+int dev_upload(npswf_handle *h, DevSlot &s, const Tp **dst, const Tp *src, size_t count)
+{
+    Tp *p = nullptr;
+    int rc = dev_alloc(h, s, &p, count);
+    if (rc) return rc;
+    CU_TRY(h, cudaMemcpy(p, src, count * sizeof(Tp), cudaMemcpyHostToDevice));
+    *dst = p;
+    return 0;
+}
+
+int alloc_workspace(npswf_handle *h, DevSlot &s, Workspace &w, int64_t cap, bool io)
+{
+    w.cap = cap;
+    w.io = io;
+    const size_t nb = (size_t)cap * B;
+    int rc = 0;
+    if (io) {
+        if ((rc = dev_alloc(h, s, &w.signal, nb * T))) return rc;
+        if ((rc = dev_alloc(h, s, &w.pres, nb))) return rc;
+        if ((rc = dev_alloc(h, s, &w.corr, (size_t)cap))) return rc;
+        if ((rc = dev_alloc(h, s, &w.wfnpulse, nb))) return rc;
+        if ((rc = dev_alloc(h, s, &w.wftime, nb * MAXP))) return rc;
+        if ((rc = dev_alloc(h, s, &w.wfampl, nb * MAXP))) return rc;
+        if ((rc = dev_alloc(h, s, &w.chi2, nb))) return rc;
+        if ((rc = dev_alloc(h, s, &w.timewf, nb))) return rc;
+        if ((rc = dev_alloc(h, s, &w.amplwf, nb))) return rc;
+        if ((rc = dev_alloc(h, s, &w.status, nb))) return rc;
+        if ((rc = dev_alloc(h, s, &w.mask, nb))) return rc;
+    }
+    if ((rc = dev_alloc(h, s, &w.mf, nb * T))) return rc;
+    if ((rc = dev_alloc(h, s, &w.minsig, nb))) return rc;
+    if ((rc = dev_alloc(h, s, &w.flags, nb))) return rc;
+    if ((rc = dev_alloc(h, s, &w.fit_count, 16))) return rc;
+    if ((rc = dev_alloc(h, s, &w.fit_list, (size_t)(MAXP + 1) * nb))) return rc;
+    CU_TRY(h, cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+    return 0;
+}
+
+// Lazily allocate the staging buffers used by the host-buffer entry points.
+int ensure_io(npswf_handle *h, DevSlot &s)
+{
+    for (int i = 0; i < 2; i++) {
+        Workspace &w = s.ws[i];
+        if (w.io) continue;
+        const size_t nb = (size_t)w.cap * B;
+        int rc = 0;
+        if ((rc = dev_alloc(h, s, &w.signal, nb * T))) return rc;
+        if ((rc = dev_alloc(h, s, &w.pres, nb))) return rc;
+        if ((rc = dev_alloc(h, s, &w.corr, (size_t)w.cap))) return rc;
+        if ((rc = dev_alloc(h, s, &w.wfnpulse, nb))) return rc;
+        if ((rc = dev_alloc(h, s, &w.wftime, nb * MAXP))) return rc;
+        if ((rc = dev_alloc(h, s, &w.wfampl, nb * MAXP))) return rc;
+        if ((rc = dev_alloc(h, s, &w.chi2, nb))) return rc;
+        if ((rc = dev_alloc(h, s, &w.timewf, nb))) return rc;
+        if ((rc = dev_alloc(h, s, &w.amplwf, nb))) return rc;
+        if ((rc = dev_alloc(h, s, &w.status, nb))) return rc;
+        if ((rc = dev_alloc(h, s, &w.mask, nb))) return rc;
+        w.io = true;
+    }
+    return 0;
+}
+
+__global__ void widen_counts_kernel(const int16_t *__restrict__ c, double *__restrict__ out, double lsb, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __dmul_rn((double)c[i], lsb);
+}
+
+// job lists from an explicit mask (npswf_fitwf_batch): one thread per (event, block)
+__global__ void build_jobs_kernel(const uint8_t *__restrict__ mask, const int32_t *__restrict__ wfnpulse, long long n_items,
+                                  int *__restrict__ fit_count, int *__restrict__ fit_list, long long stride,
+                                  double *__restrict__ chi2, uint8_t *__restrict__ status)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    chi2[i] = -100.0;
+    status[i] = 0;
+    int n = wfnpulse[i];
+    if (n > MAXP) n = MAXP;
+    if (mask[i] && n > 0) {
+        const int idx = atomicAdd(&fit_count[n], 1);
+        fit_list[(size_t)n * stride + idx] = (int)i;
+    }
+}
+
+int launch_front(npswf_handle *h, DevSlot &s, cudaStream_t st, const double *sig, const int32_t *pres, int64_t n,
+                 float *mf, double *minsig, uint8_t *flags, int do_mf, int do_thr)
+{
+    const int grid = (int)std::min<int64_t>(n, (int64_t)s.sm_count * 2 * 4);
+    front_kernel<<<grid, FRONT_THREADS, FRONT_SMEM, st>>>(sig, pres, n, s.cal, h->kp, mf, minsig, flags, do_mf, do_thr);
+    CU_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, const double *sig, const double *corr,
+                double *wftime, double *wfampl, double *chi2, double *timewf, double *amplwf, uint8_t *status)
+{
+    const long long stride = (long long)w.cap * B;
+    for (int N = 1; N <= MAXP; N++) {
+        const int *list = w.fit_list + (size_t)N * stride;
+        const int *cnt = w.fit_count + N;
+        if (N <= 3) {
+            const int grid = s.sm_count * 8;
+            fit_kernel<7><<<grid, FIT_THREADS, sizeof(FitSmem<7>) * FIT_WARPS, st>>>(
+                list, cnt, N, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr);
+        } else {
+            const int grid = s.sm_count * 2;
+            fit_kernel<25><<<grid, FIT_THREADS, sizeof(FitSmem<25>) * FIT_WARPS, st>>>(
+                list, cnt, N, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr);
+        }
+        CU_TRY(h, cudaGetLastError());
+    }
+    return 0;
+}
+
+// The whole per-chunk pipeline on device pointers: front -> search -> fits.
+int run_chunk(npswf_handle *h, DevSlot &s, Workspace &w, cudaStream_t st, int64_t n, const double *sig,
+              const int32_t *pres, const double *corr, int32_t *wfnpulse, double *wftime, double *wfampl, double *chi2,
+              double *timewf, double *amplwf, uint8_t *status)
+{
+    CU_TRY(h, cudaMemsetAsync(w.fit_count, 0, 16 * sizeof(int), st));
+    int rc = launch_front(h, s, st, sig, pres, n, w.mf, w.minsig, w.flags, 1, 1);
+    if (rc) return rc;
+    const long long items = (long long)n * B;
+    const int grid = (int)std::min<long long>((items + SEARCH_WARPS - 1) / SEARCH_WARPS, (long long)s.sm_count * 4 * 8);
+    search_kernel<<<grid, SEARCH_THREADS, SEARCH_SMEM, st>>>(w.mf, w.flags, w.minsig, sig, items, h->kp, wfnpulse, wftime,
+                                                            wfampl, chi2, timewf, amplwf, status, w.fit_count,
+                                                            w.fit_list, (long long)w.cap * B, s.ctr);
+    CU_TRY(h, cudaGetLastError());
+    return launch_fits(h, s, st, w, sig, corr, wftime, wfampl, chi2, timewf, amplwf, status);
+}
+
+template <class F>
+int for_each_slot_range(npswf_handle *h, int64_t n_events, F &&fn)
+{
+    const int nd = (int)h->slots.size();
+    if (nd == 1) return fn(0, (int64_t)0, n_events);
+    std::vector<int> rcs(nd, 0);
+    std::vector<std::thread> th;
+    for (int d = 0; d < nd; d++) {
+        const int64_t lo = n_events * d / nd, hi = n_events * (d + 1) / nd;  // contiguous event ranges
+        th.emplace_back([&, d, lo, hi]() { rcs[d] = (hi > lo) ? fn(d, lo, hi) : 0; });
+    }
+    for (auto &t : th) t.join();
+    for (int rc : rcs)
+        if (rc) return rc;
+    return 0;
+}
+
+struct HostIO {
+    const double *signal = nullptr;
+    const int16_t *counts = nullptr;
+    double lsb = 0;
+    const int32_t *pres = nullptr;
+    const double *corr = nullptr;
+    int32_t *wfnpulse = nullptr;
+    double *wftime = nullptr, *wfampl = nullptr, *chi2 = nullptr, *timewf = nullptr, *amplwf = nullptr;
+    uint8_t *status = nullptr;
+};
+
+// Chunked, double-buffered host pipeline on one device for events [lo, hi).
+int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &io)
+{
+    DevSlot &s = h->slots[d];
+    CU_TRY(h, cudaSetDevice(s.device));
+    int rc = ensure_io(h, s);
+    if (rc) return rc;
+    int which = 0;
+    for (int64_t e0 = lo; e0 < hi; e0 += h->chunk, which ^= 1) {
+        Workspace &w = s.ws[which];
+        cudaStream_t st = w.stream;
+        const int64_t n = std::min<int64_t>(h->chunk, hi - e0);
+        const size_t nb = (size_t)n * B, ob = (size_t)e0 * B;
+        if (io.counts) {
+            if (!w.counts) {
+                if ((rc = dev_alloc(h, s, &w.counts, (size_t)w.cap * B * T))) return rc;
+            }
+            CU_TRY(h, cudaMemcpyAsync(w.counts, io.counts + ob * T, nb * T * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+            const long long tot = (long long)nb * T;
+            widen_counts_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(w.counts, w.signal, io.lsb, tot);
+            CU_TRY(h, cudaGetLastError());
+        } else {
+            CU_TRY(h, cudaMemcpyAsync(w.signal, io.signal + ob * T, nb * T * sizeof(double), cudaMemcpyHostToDevice, st));
+        }
+        CU_TRY(h, cudaMemcpyAsync(w.pres, io.pres + ob, nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        if (io.corr) CU_TRY(h, cudaMemcpyAsync(w.corr, io.corr + e0, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+        else CU_TRY(h, cudaMemsetAsync(w.corr, 0, (size_t)n * sizeof(double), st));
+        rc = run_chunk(h, s, w, st, n, w.signal, w.pres, w.corr, w.wfnpulse, w.wftime, w.wfampl, w.chi2, w.timewf,
+                       w.amplwf, w.status);
+        if (rc) return rc;
+        if (io.wfnpulse) CU_TRY(h, cudaMemcpyAsync(io.wfnpulse + ob, w.wfnpulse, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (io.wftime) CU_TRY(h, cudaMemcpyAsync(io.wftime + ob * MAXP, w.wftime, nb * MAXP * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (io.wfampl) CU_TRY(h, cudaMemcpyAsync(io.wfampl + ob * MAXP, w.wfampl, nb * MAXP * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (io.chi2) CU_TRY(h, cudaMemcpyAsync(io.chi2 + ob, w.chi2, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (io.timewf) CU_TRY(h, cudaMemcpyAsync(io.timewf + ob, w.timewf, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (io.amplwf) CU_TRY(h, cudaMemcpyAsync(io.amplwf + ob, w.amplwf, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (io.status) CU_TRY(h, cudaMemcpyAsync(io.status + ob, w.status, nb * sizeof(uint8_t), cudaMemcpyDeviceToHost, st));
+    }
+    CU_TRY(h, cudaStreamSynchronize(s.ws[0].stream));
+    CU_TRY(h, cudaStreamSynchronize(s.ws[1].stream));
+    return 0;
+}
+
+int check_handle(npswf_handle *h)
+{
+    if (!h) return NPSWF_ERR_ARG;
+    if (h->slots.empty()) {
+        h->err = "handle has no usable CUDA device";
+        return NPSWF_ERR_CUDA;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+void npswf_default_config(NpsWfConfig *cfg)
+{
+    if (!cfg) return;
+    std::memset(cfg, 0, sizeof *cfg);
+    cfg->specthres = 0.02;   // T2:70
+    cfg->mfthres = 1.5;      // T2:71
+    cfg->trig_thres = 10;    // T2:72
+    cfg->coinc_width = 20;   // T2:73
+    cfg->dt = 4.0;           // T2:354
+    cfg->timerefacc = 0;     // T2:81
+    cfg->n_devices = 1;
+    cfg->devices = nullptr;
+    cfg->chunk_events = 0;
+    cfg->fit_max_iter = 0;
+    cfg->fit_retry_max_iter = 0;
+}
+
+int npswf_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char *npswf_last_error(const npswf_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+void *npswf_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    return p;
+}
+void npswf_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **out)
+{
+    if (!cfg || !cal || !out || !cal->interpX || !cal->interpY || !cal->timeref || !cal->cortime || !cal->preswf) {
+        g_create_error = "npswf_create: null argument";
+        return NPSWF_ERR_ARG;
+    }
+    npswf_handle *h = new npswf_handle;
+    h->cfg = *cfg;
+    h->kp.specthres = cfg->specthres; h->kp.mfthres = cfg->mfthres; h->kp.trig_thres = cfg->trig_thres;
+    h->kp.dt = cfg->dt; h->kp.timerefacc = cfg->timerefacc; h->kp.coinc_width = cfg->coinc_width;
+    h->kp.fit_max_iter = cfg->fit_max_iter > 0 ? cfg->fit_max_iter : 60;
+    h->kp.fit_retry_max_iter = cfg->fit_retry_max_iter > 0 ? cfg->fit_retry_max_iter : 300;
+    h->chunk = cfg->chunk_events > 0 ? cfg->chunk_events : 592;
+    // ---- derived calibration on the host (T2:440-451 for mfyref/mfint; spline coefficients)
+    h->mfyref.assign((size_t)B * MFW, 0.0);
+    h->mfint.assign(B, 0.0);
+    h->spline.assign((size_t)B * (T - 1) * 4, 0.0);
+    h->timeref.assign(cal->timeref, cal->timeref + B);
+    std::vector<double> mfrecip(B, 0.0);
+    for (int i = 0; i < B; i++) {
+        if (cal->preswf[i] != 1) continue;
+        const double *X = cal->interpX + (size_t)i * T, *Y = cal->interpY + (size_t)i * T;
+        for (int it = 0; it < T; it++) {
+            if (std::fabs(cal->timeref[i] - X[it]) < 0.001) {
+                for (int jt = 0; jt < MFW; jt++) {
+                    const int idx = it + jt - MFLEFT;
+                    const double v = (idx >= 0 && idx < T) ? Y[idx] : 0.0;
+                    h->mfyref[(size_t)i * MFW + jt] = v;
+                    h->mfint[i] += v;
+                }
+            }
+        }
+        for (int it = 1; it < T; it++) {
+            if (!(X[it] > X[it - 1])) {
+                g_create_error = "npswf_create: interpX must be strictly increasing";
+                delete h;
+                return NPSWF_ERR_CALIB;
+            }
+        }
+        if (X[0] != 0.0 || X[T - 1] != (double)(T - 1)) {
+            // the kernels index the spline by floor(x): knots must be the sample indices 0..109
+            bool unit = true;
+            for (int it = 0; it < T; it++) unit = unit && (X[it] == (double)it);
+            if (!unit) {
+                g_create_error = "npswf_create: interpX must be the sample indices 0..109 (unit knots)";
+                delete h;
+                return NPSWF_ERR_CALIB;
+            }
+        }
+        if (h->mfint[i] == 0.0) {
+            g_create_error = "npswf_create: matched-filter integral is zero for a block with preswf=1";
+            delete h;
+            return NPSWF_ERR_CALIB;
+        }
+        mfrecip[i] = 1.0 / h->mfint[i];
+        build_spline(X, Y, &h->spline[(size_t)i * (T - 1) * 4]);
+    }
+    // ---- devices
+    int ndev_avail = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev_avail);
+    if (ce != cudaSuccess || ndev_avail == 0) {
+        // the handle still carries the host-side derived calibration (npswf_get_spline etc.);
+        // every compute entry point reports NPSWF_ERR_CUDA.  No CPU fallback.
+        h->err = std::string("no CUDA device: ") + (ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0");
+        (void)cudaGetLastError();
+        *out = h;
+        return NPSWF_OK;
+    }
+    int nd = cfg->n_devices > 0 ? cfg->n_devices : 1;
+    for (int d = 0; d < nd; d++) h->devices.push_back(cfg->devices ? cfg->devices[d] : d);
+    double ata[2 * TS_LH - 1];
+    {
+        const double resp[TS_LH] = {11, 43, 135, 324, 606, 882, 1000, 882, 606, 324, 135, 43, 11, 2};
+        for (int lag = -(TS_LH - 1); lag <= TS_LH - 1; lag++) {
+            double lda = 0;
+            for (int j = 0; j < TS_LH; j++)
+                if (j + lag >= 0 && j + lag < TS_LH) lda = lda + resp[j] * resp[j + lag];
+            ata[lag + TS_LH - 1] = lda;
+        }
+    }
+    h->slots.resize(nd);
+    for (int d = 0; d < nd; d++) {
+        DevSlot &s = h->slots[d];
+        s.device = h->devices[d];
+        auto fail = [&](int rc) {
+            g_create_error = h->err;
+            npswf_destroy(h);
+            return rc;
+        };
+#define CR(expr)                                                          \
+    do {                                                                  \
+        cudaError_t _e = (expr);                                          \
+        if (_e != cudaSuccess) {                                          \
+            h->err = std::string(#expr ": ") + cudaGetErrorString(_e);    \
+            return fail(NPSWF_ERR_CUDA);                                  \
+        }                                                                 \
+    } while (0)
+        CR(cudaSetDevice(s.device));
+        cudaDeviceProp prop;
+        CR(cudaGetDeviceProperties(&prop, s.device));
+        if (prop.major < 10) {
+            h->err = "device is not sm_100 (Blackwell B200) class";
+            return fail(NPSWF_ERR_CUDA);
+        }
+        s.sm_count = prop.multiProcessorCount;
+        int rc;
+        if ((rc = dev_upload(h, s, &s.cal.mfyref, h->mfyref.data(), h->mfyref.size()))) return fail(rc);
+        if ((rc = dev_upload(h, s, &s.cal.mfint, h->mfint.data(), h->mfint.size()))) return fail(rc);
+        if ((rc = dev_upload(h, s, &s.cal.mfrecip, mfrecip.data(), mfrecip.size()))) return fail(rc);
+        if ((rc = dev_upload(h, s, &s.cal.timeref, cal->timeref, (size_t)B))) return fail(rc);
+        if ((rc = dev_upload(h, s, &s.cal.cortime, cal->cortime, (size_t)B))) return fail(rc);
+        if ((rc = dev_upload(h, s, &s.cal.preswf, cal->preswf, (size_t)B))) return fail(rc);
+        if ((rc = dev_upload(h, s, &s.cal.spline, h->spline.data(), h->spline.size()))) return fail(rc);
+        CR(cudaMemcpyToSymbol(c_ts_ata, ata, sizeof ata));
+        if ((rc = dev_alloc(h, s, &s.ctr, 1))) return fail(rc);
+        CR(cudaMemset(s.ctr, 0, sizeof(DeviceCounters)));
+        CR(cudaStreamCreateWithFlags(&s.own_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++)
+            if ((rc = alloc_workspace(h, s, s.ws[i], h->chunk, false))) return fail(rc);
+        CR(cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRONT_SMEM));
+        CR(cudaFuncSetAttribute(search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEARCH_SMEM));
+        CR(cudaFuncSetAttribute(tspectrum_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEARCH_SMEM));
+        CR(cudaFuncSetAttribute(fit_kernel<25>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(sizeof(FitSmem<25>) * FIT_WARPS)));
+        CR(cudaFuncSetAttribute(fit_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(sizeof(FitSmem<7>) * FIT_WARPS)));
+#undef CR
+    }
+    *out = h;
+    return NPSWF_OK;
+}
+
+void npswf_destroy(npswf_handle *h)
+{
+    if (!h) return;
+    for (DevSlot &s : h->slots) {
+        cudaSetDevice(s.device);
+        cudaDeviceSynchronize();
+        for (int i = 0; i < 2; i++)
+            if (s.ws[i].stream) cudaStreamDestroy(s.ws[i].stream);
+        if (s.own_stream) cudaStreamDestroy(s.own_stream);
+        for (void *p : s.owned) cudaFree(p);
+    }
+    delete h;
+}
+
+int npswf_get_counters(npswf_handle *h, NpsWfCounters *out)
+{
+    if (!h || !out) return NPSWF_ERR_ARG;
+    NpsWfCounters c = h->host_ctr;
+    for (DevSlot &s : h->slots) {
+        DeviceCounters dc;
+        CU_TRY(h, cudaSetDevice(s.device));
+        CU_TRY(h, cudaDeviceSynchronize());
+        CU_TRY(h, cudaMemcpy(&dc, s.ctr, sizeof dc, cudaMemcpyDeviceToHost));
+        c.n_present += (int64_t)dc.n_present;
+        c.n_pass_threshold += (int64_t)dc.n_pass_threshold;
+        c.n_fit_attempted += (int64_t)dc.n_fit_attempted;
+        c.n_fit_ok_first += (int64_t)dc.n_fit_ok_first;
+        c.n_fit_ok_retry += (int64_t)dc.n_fit_ok_retry;
+        c.n_fallback += (int64_t)dc.n_fallback;
+        c.n_pulses += (int64_t)dc.n_pulses;
+        c.n_peak_buffer_full += (int64_t)dc.n_peak_buffer_full;
+        c.n_fit_iterations += (int64_t)dc.n_fit_iterations;
+    }
+    *out = c;
+    return 0;
+}
+
+int npswf_reset_counters(npswf_handle *h)
+{
+    if (!h) return NPSWF_ERR_ARG;
+    h->host_ctr = NpsWfCounters{};
+    for (DevSlot &s : h->slots) {
+        CU_TRY(h, cudaSetDevice(s.device));
+        CU_TRY(h, cudaDeviceSynchronize());
+        CU_TRY(h, cudaMemset(s.ctr, 0, sizeof(DeviceCounters)));
+    }
+    return 0;
+}
+
+int npswf_analyze_batch(npswf_handle *h, int64_t n_events, const double *signal, const int32_t *pres,
+                        const double *corr_time_HMS, int32_t *wfnpulse, double *wftime, double *wfampl, double *chi2,
+                        double *timewf, double *amplwf, uint8_t *status)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (n_events < 0 || (n_events > 0 && (!signal || !pres))) {
+        h->err = "npswf_analyze_batch: bad arguments";
+        return NPSWF_ERR_ARG;
+    }
+    if (n_events == 0) return 0;
+    HostIO io;
+    io.signal = signal; io.pres = pres; io.corr = corr_time_HMS; io.wfnpulse = wfnpulse; io.wftime = wftime;
+    io.wfampl = wfampl; io.chi2 = chi2; io.timewf = timewf; io.amplwf = amplwf; io.status = status;
+    rc = for_each_slot_range(h, n_events, [&](int d, int64_t lo, int64_t hi) { return analyze_range(h, d, lo, hi, io); });
+    if (rc) return rc;
+    h->host_ctr.n_events += n_events;
+    h->host_ctr.n_block_waveforms += n_events * B;
+    return 0;
+}
+
+int npswf_analyze_batch_i16(npswf_handle *h, int64_t n_events, const int16_t *counts, double lsb_mV,
+                            const int32_t *pres, const double *corr_time_HMS, int32_t *wfnpulse, double *wftime,
+                            double *wfampl, double *chi2, double *timewf, double *amplwf, uint8_t *status)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (n_events < 0 || (n_events > 0 && (!counts || !pres))) {
+        h->err = "npswf_analyze_batch_i16: bad arguments";
+        return NPSWF_ERR_ARG;
+    }
+    if (n_events == 0) return 0;
+    HostIO io;
+    io.counts = counts; io.lsb = lsb_mV; io.pres = pres; io.corr = corr_time_HMS; io.wfnpulse = wfnpulse;
+    io.wftime = wftime; io.wfampl = wfampl; io.chi2 = chi2; io.timewf = timewf; io.amplwf = amplwf; io.status = status;
+    rc = for_each_slot_range(h, n_events, [&](int d, int64_t lo, int64_t hi) { return analyze_range(h, d, lo, hi, io); });
+    if (rc) return rc;
+    h->host_ctr.n_events += n_events;
+    h->host_ctr.n_block_waveforms += n_events * B;
+    return 0;
+}
+
+int npswf_analyze_batch_device(npswf_handle *h, int32_t dev_slot, int64_t n_events, const double *d_signal,
+                               const int32_t *d_pres, const double *d_corr, int32_t *d_wfnpulse, double *d_wftime,
+                               double *d_wfampl, double *d_chi2, double *d_timewf, double *d_amplwf, uint8_t *d_status,
+                               void *stream)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (dev_slot < 0 || dev_slot >= (int)h->slots.size() || n_events < 0 || !d_signal || !d_pres || !d_wftime ||
+        !d_wfampl || !d_chi2 || !d_status) {
+        h->err = "npswf_analyze_batch_device: bad arguments (wftime/wfampl/chi2/status are required)";
+        return NPSWF_ERR_ARG;
+    }
+    if (((uintptr_t)d_signal & 15) != 0) {
+        h->err = "npswf_analyze_batch_device: d_signal must be 16-byte aligned (bulk TMA source)";
+        return NPSWF_ERR_ARG;
+    }
+    DevSlot &s = h->slots[dev_slot];
+    CU_TRY(h, cudaSetDevice(s.device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s.own_stream;
+    Workspace &w = s.ws[0];
+    for (int64_t e0 = 0; e0 < n_events; e0 += w.cap) {
+        const int64_t n = std::min<int64_t>(w.cap, n_events - e0);
+        const size_t ob = (size_t)e0 * B;
+        rc = run_chunk(h, s, w, st, n, d_signal + ob * T, d_pres + ob, d_corr ? d_corr + e0 : nullptr,
+                       d_wfnpulse ? d_wfnpulse + ob : nullptr, d_wftime + ob * MAXP, d_wfampl + ob * MAXP, d_chi2 + ob,
+                       d_timewf ? d_timewf + ob : nullptr, d_amplwf ? d_amplwf + ob : nullptr, d_status + ob);
+        if (rc) return rc;
+    }
+    h->host_ctr.n_events += n_events;
+    h->host_ctr.n_block_waveforms += n_events * B;
+    return 0;
+}
+
+int npswf_sync_device(npswf_handle *h, int32_t dev_slot, void *stream)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (dev_slot < 0 || dev_slot >= (int)h->slots.size()) return NPSWF_ERR_ARG;
+    DevSlot &s = h->slots[dev_slot];
+    CU_TRY(h, cudaSetDevice(s.device));
+    CU_TRY(h, cudaStreamSynchronize(stream ? (cudaStream_t)stream : s.own_stream));
+    return 0;
+}
+
+// ---- stage-level entry points: single device (slot 0), chunked, synchronous ----
+
+int npswf_find_pulses_mf_batch(npswf_handle *h, int64_t n_events, const double *signal, const int32_t *pres,
+                               int32_t *wfnpulse, double *wftime, double *wfampl)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (n_events < 0 || (n_events > 0 && (!signal || !pres || !wfnpulse || !wftime || !wfampl))) return NPSWF_ERR_ARG;
+    DevSlot &s = h->slots[0];
+    CU_TRY(h, cudaSetDevice(s.device));
+    if ((rc = ensure_io(h, s))) return rc;
+    Workspace &w = s.ws[0];
+    cudaStream_t st = w.stream;
+    for (int64_t e0 = 0; e0 < n_events; e0 += w.cap) {
+        const int64_t n = std::min<int64_t>(w.cap, n_events - e0);
+        const size_t nb = (size_t)n * B, ob = (size_t)e0 * B;
+        CU_TRY(h, cudaMemcpyAsync(w.signal, signal + ob * T, nb * T * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU_TRY(h, cudaMemcpyAsync(w.pres, pres + ob, nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        if ((rc = launch_front(h, s, st, w.signal, w.pres, n, w.mf, w.minsig, w.flags, 1, 0))) return rc;
+        const long long items = (long long)nb;
+        const int grid = (int)std::min<long long>((items + SEARCH_WARPS - 1) / SEARCH_WARPS, (long long)s.sm_count * 32);
+        search_kernel<<<grid, SEARCH_THREADS, SEARCH_SMEM, st>>>(w.mf, w.flags, w.minsig, w.signal, items, h->kp, w.wfnpulse,
+                                                                w.wftime, w.wfampl, nullptr, nullptr, nullptr, nullptr,
+                                                                nullptr, nullptr, 0, nullptr);
+        CU_TRY(h, cudaGetLastError());
+        CU_TRY(h, cudaMemcpyAsync(wfnpulse + ob, w.wfnpulse, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CU_TRY(h, cudaMemcpyAsync(wftime + ob * MAXP, w.wftime, nb * MAXP * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU_TRY(h, cudaMemcpyAsync(wfampl + ob * MAXP, w.wfampl, nb * MAXP * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU_TRY(h, cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+int npswf_pass_cluster_threshold_batch(npswf_handle *h, int64_t n_events, const double *signal, const int32_t *pres,
+                                       uint8_t *ok)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (n_events < 0 || (n_events > 0 && (!signal || !pres || !ok))) return NPSWF_ERR_ARG;
+    DevSlot &s = h->slots[0];
+    CU_TRY(h, cudaSetDevice(s.device));
+    if ((rc = ensure_io(h, s))) return rc;
+    Workspace &w = s.ws[0];
+    cudaStream_t st = w.stream;
+    std::vector<uint8_t> tmp;
+    for (int64_t e0 = 0; e0 < n_events; e0 += w.cap) {
+        const int64_t n = std::min<int64_t>(w.cap, n_events - e0);
+        const size_t nb = (size_t)n * B, ob = (size_t)e0 * B;
+        CU_TRY(h, cudaMemcpyAsync(w.signal, signal + ob * T, nb * T * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU_TRY(h, cudaMemcpyAsync(w.pres, pres + ob, nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        if ((rc = launch_front(h, s, st, w.signal, w.pres, n, nullptr, nullptr, w.flags, 0, 1))) return rc;
+        tmp.resize(nb);
+        CU_TRY(h, cudaMemcpyAsync(tmp.data(), w.flags, nb, cudaMemcpyDeviceToHost, st));
+        CU_TRY(h, cudaStreamSynchronize(st));
+        for (size_t i = 0; i < nb; i++) ok[ob + i] = (tmp[i] & FL_OKTOFIT) ? 1 : 0;
+    }
+    return 0;
+}
+
+int npswf_matched_filter_batch(npswf_handle *h, int64_t n_events, const double *signal, const int32_t *pres, float *mf)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (n_events < 0 || (n_events > 0 && (!signal || !pres || !mf))) return NPSWF_ERR_ARG;
+    DevSlot &s = h->slots[0];
+    CU_TRY(h, cudaSetDevice(s.device));
+    if ((rc = ensure_io(h, s))) return rc;
+    Workspace &w = s.ws[0];
+    cudaStream_t st = w.stream;
+    for (int64_t e0 = 0; e0 < n_events; e0 += w.cap) {
+        const int64_t n = std::min<int64_t>(w.cap, n_events - e0);
+        const size_t nb = (size_t)n * B, ob = (size_t)e0 * B;
+        CU_TRY(h, cudaMemcpyAsync(w.signal, signal + ob * T, nb * T * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU_TRY(h, cudaMemcpyAsync(w.pres, pres + ob, nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CU_TRY(h, cudaMemsetAsync(w.mf, 0, nb * T * sizeof(float), st));
+        if ((rc = launch_front(h, s, st, w.signal, w.pres, n, w.mf, w.minsig, w.flags, 1, 0))) return rc;
+        CU_TRY(h, cudaMemcpyAsync(mf + ob * T, w.mf, nb * T * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU_TRY(h, cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+int npswf_fitwf_batch(npswf_handle *h, int64_t n_events, const double *signal, const double *corr_time_HMS,
+                      const uint8_t *fit_mask, const int32_t *wfnpulse, double *wftime, double *wfampl, double *chi2,
+                      uint8_t *status)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (n_events < 0 || (n_events > 0 && (!signal || !fit_mask || !wfnpulse || !wftime || !wfampl || !chi2 || !status)))
+        return NPSWF_ERR_ARG;
+    DevSlot &s = h->slots[0];
+    CU_TRY(h, cudaSetDevice(s.device));
+    if ((rc = ensure_io(h, s))) return rc;
+    Workspace &w = s.ws[0];
+    cudaStream_t st = w.stream;
+    for (int64_t e0 = 0; e0 < n_events; e0 += w.cap) {
+        const int64_t n = std::min<int64_t>(w.cap, n_events - e0);
+        const size_t nb = (size_t)n * B, ob = (size_t)e0 * B;
+        CU_TRY(h, cudaMemcpyAsync(w.signal, signal + ob * T, nb * T * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (corr_time_HMS) CU_TRY(h, cudaMemcpyAsync(w.corr, corr_time_HMS + e0, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+        else CU_TRY(h, cudaMemsetAsync(w.corr, 0, (size_t)n * sizeof(double), st));
+        CU_TRY(h, cudaMemcpyAsync(w.mask, fit_mask + ob, nb, cudaMemcpyHostToDevice, st));
+        CU_TRY(h, cudaMemcpyAsync(w.wfnpulse, wfnpulse + ob, nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CU_TRY(h, cudaMemcpyAsync(w.wftime, wftime + ob * MAXP, nb * MAXP * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU_TRY(h, cudaMemcpyAsync(w.wfampl, wfampl + ob * MAXP, nb * MAXP * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU_TRY(h, cudaMemsetAsync(w.fit_count, 0, 16 * sizeof(int), st));
+        build_jobs_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(w.mask, w.wfnpulse, (long long)nb, w.fit_count,
+                                                                       w.fit_list, (long long)w.cap * B, w.chi2, w.status);
+        CU_TRY(h, cudaGetLastError());
+        if ((rc = launch_fits(h, s, st, w, w.signal, w.corr, w.wftime, w.wfampl, w.chi2, nullptr, nullptr, w.status))) return rc;
+        CU_TRY(h, cudaMemcpyAsync(wftime + ob * MAXP, w.wftime, nb * MAXP * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU_TRY(h, cudaMemcpyAsync(wfampl + ob * MAXP, w.wfampl, nb * MAXP * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU_TRY(h, cudaMemcpyAsync(chi2 + ob, w.chi2, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU_TRY(h, cudaMemcpyAsync(status + ob, w.status, nb, cudaMemcpyDeviceToHost, st));
+        CU_TRY(h, cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+int npswf_tspectrum_debug(npswf_handle *h, int64_t n, const float *hist, int32_t *npeaks, double *pos_x, double *smoothed,
+                          double *decon)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && !hist)) return NPSWF_ERR_ARG;
+    if (n == 0) return 0;
+    DevSlot &s = h->slots[0];
+    CU_TRY(h, cudaSetDevice(s.device));
+    float *d_h = nullptr;
+    int32_t *d_n = nullptr;
+    double *d_p = nullptr, *d_s = nullptr, *d_d = nullptr;
+    CU_TRY(h, cudaMalloc(&d_h, (size_t)n * T * sizeof(float)));
+    CU_TRY(h, cudaMalloc(&d_n, (size_t)n * sizeof(int32_t)));
+    CU_TRY(h, cudaMalloc(&d_p, (size_t)n * MAXP * sizeof(double)));
+    CU_TRY(h, cudaMalloc(&d_s, (size_t)n * TS_S * sizeof(double)));
+    CU_TRY(h, cudaMalloc(&d_d, (size_t)n * T * sizeof(double)));
+    CU_TRY(h, cudaMemcpy(d_h, hist, (size_t)n * T * sizeof(float), cudaMemcpyHostToDevice));
+    const int grid = (int)std::min<long long>((n + SEARCH_WARPS - 1) / SEARCH_WARPS, (long long)s.sm_count * 32);
+    tspectrum_debug_kernel<<<grid, SEARCH_THREADS, SEARCH_SMEM>>>(d_h, n, 100.0 * h->kp.specthres, d_n, d_p, d_s, d_d);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaDeviceSynchronize());
+    if (npeaks) CU_TRY(h, cudaMemcpy(npeaks, d_n, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (pos_x) CU_TRY(h, cudaMemcpy(pos_x, d_p, (size_t)n * MAXP * sizeof(double), cudaMemcpyDeviceToHost));
+    if (smoothed) CU_TRY(h, cudaMemcpy(smoothed, d_s, (size_t)n * TS_S * sizeof(double), cudaMemcpyDeviceToHost));
+    if (decon) CU_TRY(h, cudaMemcpy(decon, d_d, (size_t)n * T * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(d_h); cudaFree(d_n); cudaFree(d_p); cudaFree(d_s); cudaFree(d_d);
+    return 0;
+}
+
+int npswf_debug_exp(npswf_handle *h, int64_t n, const double *x, double *y)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (n <= 0 || !x || !y) return NPSWF_ERR_ARG;
+    DevSlot &s = h->slots[0];
+    CU_TRY(h, cudaSetDevice(s.device));
+    double *dx = nullptr, *dy = nullptr;
+    CU_TRY(h, cudaMalloc(&dx, (size_t)n * 8));
+    CU_TRY(h, cudaMalloc(&dy, (size_t)n * 8));
+    CU_TRY(h, cudaMemcpy(dx, x, (size_t)n * 8, cudaMemcpyHostToDevice));
+    det_exp_debug_kernel<<<(unsigned)((n + 255) / 256), 256>>>(dx, dy, n);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaMemcpy(y, dy, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(dy);
+    return 0;
+}
+
+int npswf_get_mf_calib(const npswf_handle *h, double *mfyref, double *mfint)
+{
+    if (!h || !mfyref || !mfint) return NPSWF_ERR_ARG;
+    std::memcpy(mfyref, h->mfyref.data(), h->mfyref.size() * sizeof(double));
+    std::memcpy(mfint, h->mfint.data(), h->mfint.size() * sizeof(double));
+    return 0;
+}
+
+int npswf_get_spline(const npswf_handle *h, double *coef)
+{
+    if (!h || !coef) return NPSWF_ERR_ARG;
+    std::memcpy(coef, h->spline.data(), h->spline.size() * sizeof(double));
+    return 0;
+}
+
+const double *npswf_device_spline(const npswf_handle *h, int32_t dev_slot)
+{
+    if (!h || dev_slot < 0 || dev_slot >= (int)h->slots.size()) return nullptr;
+    return h->slots[dev_slot].cal.spline;
+}
+const double *npswf_device_timeref(const npswf_handle *h, int32_t dev_slot)
+{
+    if (!h || dev_slot < 0 || dev_slot >= (int)h->slots.size()) return nullptr;
+    return h->slots[dev_slot].cal.timeref;
+}
+
+int64_t npswf_flatten_event(const int32_t *wfnpulse, const double *wftime_padded, const double *wfampl_padded,
+                            double *wftime_flat, double *wfampl_flat, int32_t *block_offset)
+{
+    int64_t off = 0;
+    for (int i = 0; i < B; i++) {
+        if (block_offset) block_offset[i] = (int32_t)off;  // T2:959
+        const int n = wfnpulse[i];
+        for (int p = 0; p < n && p < MAXP; p++) {
+            if (wftime_flat) wftime_flat[off + p] = wftime_padded[(size_t)i * MAXP + p];
+            if (wfampl_flat) wfampl_flat[off + p] = wfampl_padded[(size_t)i * MAXP + p];
+        }
+        off += (n < MAXP ? n : MAXP);  // T2:961
+    }
+    if (block_offset) block_offset[B] = (int32_t)off;  // T2:1022
+    return off;
+}
+
+}  // extern "C"

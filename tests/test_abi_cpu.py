@@ -1,0 +1,90 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol include/npswf.h declares,
+derives the same calibration as the oracle, and refuses to compute without a GPU (no fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    hdr = open(os.path.join(ROOT, "include", "npswf.h")).read()
+    declared = sorted(set(re.findall(r"\b(npswf_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 20
+    L = pkg.lib()
+    for name in declared:
+        assert hasattr(L, name), "libnpswf.so does not export %s" % name
+    assert sorted(pkg.EXPORTS) == declared
+
+
+def test_struct_layout_matches_header(pkg):
+    assert C.sizeof(pkg.NpsWfConfig) == 80
+    assert C.sizeof(pkg.NpsWfCalib) == 40
+    assert C.sizeof(pkg.NpsWfCounters) == 88
+
+
+def test_derived_calibration_matches_oracle(pkg, calib, orc):
+    h = pkg.NpsWf(calib)
+    y, i = h.mf_calib()
+    oy, oi = orc.mf_calib()
+    assert np.array_equal(y, oy) and np.array_equal(i, oi)      # T2:440-451, bitwise
+    assert np.abs(h.spline_coeffs() - orc.spline_coeffs()).max() < 1e-14
+
+
+def test_bad_calibration_is_rejected(pkg, calib):
+    bad = dict(calib)
+    bad["interpX"] = calib["interpX"] * 0.5
+    with pytest.raises(pkg.NpsWfError) as ei:
+        pkg.NpsWf(bad)
+    assert ei.value.code == pkg.ERR_CALIB
+
+
+def test_no_cpu_fallback(pkg, calib):
+    """Without a usable GPU every compute entry point must fail loudly with NPSWF_ERR_CUDA."""
+    if pkg.lib().npswf_device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    h = pkg.NpsWf(calib)
+    sig = np.zeros((1, 1080, 110)); pres = np.ones((1, 1080), np.int32)
+    for call in (lambda: h.analyze(sig, pres, np.zeros(1)), lambda: h.FindPulsesMF(sig, pres),
+                 lambda: h.PassClusterThreshold(sig, pres), lambda: h.matched_filter(sig, pres),
+                 lambda: h.tspectrum_debug(np.zeros((1, 110), np.float32))):
+        with pytest.raises(pkg.NpsWfError) as ei:
+            call()
+        assert ei.value.code == pkg.ERR_CUDA
+
+
+def test_flatten_event_matches_reference_packing(pkg):
+    """blockOffset / flattened wfampl, wftime as at T2:959-961, 1022, 1294-1295."""
+    rng = np.random.default_rng(5)
+    n = rng.integers(0, 5, 1080).astype(np.int32)
+    n[rng.random(1080) < 0.5] = 0
+    t = rng.normal(size=(1080, 12)); a = rng.normal(size=(1080, 12))
+    tf, af, off = pkg.flatten_event(n, t, a)
+    assert off[0] == 0 and off[-1] == n.sum() and np.array_equal(np.diff(off), n)
+    exp_t = np.concatenate([t[b, :n[b]] for b in range(1080)])
+    exp_a = np.concatenate([a[b, :n[b]] for b in range(1080)])
+    assert np.array_equal(tf, exp_t) and np.array_equal(af, exp_a)
+    tf0, af0, off0 = pkg.flatten_event(np.zeros(1080, np.int32), t, a)   # empty event
+    assert tf0.size == 0 and off0[-1] == 0
+
+
+def test_shard_range_partitions_events(pkg):
+    for n in (0, 1, 7, 1000, 10_000_001):
+        for w in (1, 2, 3, 8):
+            r = [pkg.shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[k][1] == r[k + 1][0] for k in range(w - 1))
+            assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+
+
+def test_synth_lattice_and_determinism(calib, spline):
+    import synth
+    p = synth.config_params(2, absent_frac=0.1)
+    a = synth.generate_host(p, spline, calib, 5, 2, n_threads=2, counts=True)
+    b = synth.generate_host(p, spline, calib, 6, 1, n_threads=1, counts=True)
+    assert np.array_equal(a["signal"][1], b["signal"][0])               # keyed by (seed, event, block)
+    assert np.array_equal(a["counts"] * synth.LSB, a["signal"])         # exact on the ADC lattice
+    assert (a["signal"][a["pres"] == 0] == 0).all() and 0.05 < (a["pres"] == 0).mean() < 0.15
