@@ -1,0 +1,354 @@
+#!/usr/bin/env python3
+"""bench.py — fitted block-waveforms/s of the NPS waveform hot path on N B200s (one process per GPU).
+
+Workload (BASELINE.json configs[1]): synthetic events, 1-3 pulses/block with pile-up, all 1080 blocks
+present, generated ON DEVICE (synth/) into resident HBM batches.  A "step" is one pass of the full
+pipeline (matched filter -> TSpectrum search -> 3x3 cluster threshold -> template fit) over one batch.
+
+  value : whole-job fitted block-waveforms/s with inputs resident in HBM (device-timed, max over ranks)
+  e2e   : the same metric through the reference-facing C-ABI call npswf_analyze_batch with pinned HOST
+          buffers; H2D of the inputs and D2H of every output are inside the timed region
+  roofline / stages : per-kernel CUDA-event times taken inside the timed region (library profiling
+          hooks record events on the launching stream), algorithmic bytes per SURVEY.md §8(d)
+  cpu_baseline : the CPU oracle (a port/restatement of the reference path — ROOT is not installable)
+          on the box's host cores, on a bounded sample of the same workload
+
+--impl reference times that CPU restatement alone (all host threads) and prints the same JSON line.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NB, NT, MAXP = 1080, 110, 12
+METRIC = "fitted block-waveforms/sec"
+UNIT = "block-waveforms/s"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload_string(batch, steps):
+    return ("BASELINE configs[1]: synthetic events x 1080 blocks x 110 samples, 1-3 pulses/block with pile-up "
+            "(A~logU[3,500] mV, sep>=3 bins, sigma=0.30 mV, 12-bit ADC lattice), all blocks present; "
+            "%d events/step/GPU, %d steps" % (batch, steps))
+
+
+def run_reference(args, rank, world):
+    """CPU restatement of the reference path (oracle port), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    import oracle
+    import synth
+    cal = synth.make_calibration()
+    orc = oracle.Oracle(cal)
+    spl = orc.spline_coeffs()
+    threads = os.cpu_count() or 1
+    n_ev = args.ref_events
+    p = synth.config_params(2)
+    times, fitted = [], 0
+    for s in range(args.warmup + args.steps):
+        ev = synth.generate_host(p, spl, cal, 10_000_000 + s * n_ev, n_ev, n_threads=threads)
+        t0 = time.perf_counter()
+        r = orc.analyze_batch(ev["signal"], ev["pres"], ev["corr_time_HMS"], n_threads=threads)
+        dt = time.perf_counter() - t0
+        if s >= args.warmup:
+            times.append(dt)
+            fitted += int(((r["status"] & 28) > 0).sum())
+    total = float(sum(times))
+    value = fitted / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, len(times)), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_string(n_ev, args.steps),
+                   "note": "CPU restatement of npsWF.C's path (TSpectrum + Minuit2-Migrad restated; ROOT is not "
+                           "installable here); std::thread pool over events mirrors EnableImplicitMT"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d events/step x %d steps of the same workload" % (n_ev, args.steps)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch-events", type=int, default=2368, help="events per step per GPU (multiple of 592)")
+    ap.add_argument("--e2e-events", type=int, default=1184, help="events per end-to-end step per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--ref-events", type=int, default=24, help="--impl reference: events per step")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import synth
+    pkg = importlib.import_module("nps-waveform-analysis_b200")
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    cal = synth.make_calibration()
+    h = pkg.NpsWf(cal, devices=[local_rank])
+    E = args.batch_events
+    p = synth.config_params(2)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    st = stream.cuda_stream
+    d_spl = torch.from_numpy(h.spline_coeffs()).to(dev)
+    d_tref = torch.from_numpy(cal["timeref"]).to(dev)
+    d_kap = torch.from_numpy(cal["kappa"]).to(dev)
+
+    n_buf = 2   # two distinct resident batches, alternated; each is far larger than the 126 MB L2
+    bufs = []
+    for b in range(n_buf):
+        sig = torch.empty((E, NB, NT), dtype=torch.float64, device=dev)
+        pres = torch.empty((E, NB), dtype=torch.int32, device=dev)
+        corr = torch.empty((E,), dtype=torch.float64, device=dev)
+        ev0 = (rank * n_buf + b) * E     # contiguous, disjoint event ranges per rank (weak scaling)
+        synth.generate_device(p, d_spl.data_ptr(), d_tref.data_ptr(), d_kap.data_ptr(), ev0, E, sig.data_ptr(), 0,
+                              pres.data_ptr(), corr.data_ptr(), st)
+        bufs.append((sig, pres, corr))
+    out = dict(wfnpulse=torch.empty((E, NB), dtype=torch.int32, device=dev),
+               wftime=torch.empty((E, NB, MAXP), dtype=torch.float64, device=dev),
+               wfampl=torch.empty((E, NB, MAXP), dtype=torch.float64, device=dev),
+               chi2=torch.empty((E, NB), dtype=torch.float64, device=dev),
+               timewf=torch.empty((E, NB), dtype=torch.float64, device=dev),
+               amplwf=torch.empty((E, NB), dtype=torch.float64, device=dev),
+               status=torch.empty((E, NB), dtype=torch.uint8, device=dev))
+    torch.cuda.synchronize()
+
+    def step(i):
+        sig, pres, corr = bufs[i % n_buf]
+        h.analyze_device(E, sig.data_ptr(), pres.data_ptr(), corr.data_ptr(), out["wfnpulse"].data_ptr(),
+                         out["wftime"].data_ptr(), out["wfampl"].data_ptr(), out["chi2"].data_ptr(),
+                         out["timewf"].data_ptr(), out["amplwf"].data_ptr(), out["status"].data_ptr(), stream=st)
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    h.sync_device(stream=st)
+    h.reset_counters()
+    h.stage_times(reset=True)
+    h.set_profiling(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    h.sync_device(stream=st)
+    h.set_profiling(False)
+    ms_total = e0.elapsed_time(e1)
+    stages = h.stage_times(reset=True)
+    ctr = h.counters()
+    fitted_local = ctr["n_fit_attempted"]
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([fitted_local, ctr["n_block_waveforms"], ctr["n_pulses"], ctr["n_fit_iterations"],
+                        ctr["n_fallback"], ctr["n_fit_ok_retry"]], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms_total = float(t.item())
+    fitted, blocks, pulses, iters, n_fb, n_retry = [int(v) for v in cnt.tolist()]
+    value = fitted / (ms_total * 1e-3)
+
+    # ---- end to end through npswf_analyze_batch: pinned host buffers, H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        Ee = args.e2e_events
+        hs = pkg.pinned_empty((Ee, NB, NT), np.float64)
+        hp = pkg.pinned_empty((Ee, NB), np.int32)
+        hc = pkg.pinned_empty((Ee,), np.float64)
+        hs[...] = bufs[0][0][:Ee].cpu().numpy()
+        hp[...] = bufs[0][1][:Ee].cpu().numpy()
+        hc[...] = bufs[0][2][:Ee].cpu().numpy()
+        ho = h.alloc_outputs(Ee, pinned=True)
+        h.analyze(hs, hp, hc, out=ho)          # warm-up (allocates the staging buffers)
+        h.analyze(hs, hp, hc, out=ho)
+        h.reset_counters()
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            h.analyze(hs, hp, hc, out=ho)      # synchronous: returns when every output is in host memory
+        torch.cuda.synchronize()
+        dt_e2e = time.perf_counter() - t0
+        c2 = h.counters()
+        te = torch.tensor([dt_e2e], dtype=torch.float64, device=dev)
+        ce = torch.tensor([c2["n_fit_attempted"]], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ce, op=dist.ReduceOp.SUM)
+        h2d = hs.nbytes + hp.nbytes + hc.nbytes
+        d2h = sum(v.nbytes for v in ho.values())
+        e2e = {"value": float(ce.item()) / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "events_per_step_per_gpu": Ee, "steps": args.e2e_steps,
+               "input": "f64 [E][1080][110] (the reference's Double_t layout), pinned host memory",
+               "ms_per_step": 1e3 * float(te.item()) / args.e2e_steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel + per-stage table (rank 0's CUDA-event times inside the timed region)
+    peaks, peak_src = _peaks()
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    chunks = max(1, stages["chunks"])
+    units_local = ctr["n_block_waveforms"]
+    nbar = ctr["n_pulses"] / max(1, ctr["n_present"])
+    fit_local = max(1, ctr["n_fit_attempted"])
+    # algorithmic bytes per block-waveform, SURVEY.md §8(d) (FP64 input ABI, s = 8)
+    alg = {
+        "front": 880.0 + 1.0,                  # matched filter + 3x3 threshold: each sample once, 1 flag byte
+        "search": 440.0 + 4.0 + 16.0 * nbar,   # reads the float MF spectrum, writes wfnpulse + (t, A) per pulse
+        "fit": 880.0 + 16.0 * nbar + 13.0 + 16.0 * nbar,  # per FITTED block: trace + seeds in, chi2/status/(t, A) out
+    }
+    stage_units = {"front": units_local, "search": units_local, "fit": ctr["n_fit_attempted"]}
+    stage_rows = {}
+    for k in ("front", "search", "fit"):
+        ms = stages[k + "_ms"]
+        gbs = stage_units[k] * alg[k] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        stage_rows[k] = {"ms_per_step": ms / args.steps, "share": ms / max(1e-9, sum(stages[s + "_ms"] for s in ("front", "search", "fit"))),
+                         "alg_bytes_per_unit": alg[k], "achieved_gbs": gbs, "frac_of_hbm": gbs / hbm,
+                         "units_per_s": stage_units[k] / (ms * 1e-3) if ms > 0 else 0.0}
+    dom = max(("front", "search", "fit"), key=lambda k: stages[k + "_ms"])
+    launches_per_chunk = {"front": 1, "search": 1, "fit": 12}
+    roofline = {"kernel": {"front": "front_kernel", "search": "search_kernel", "fit": "fit_kernel<7>/<25> (12 launches)"}[dom],
+                "bound": "hbm", "achieved": stage_rows[dom]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
+                "frac": stage_rows[dom]["achieved_gbs"] / hbm, "traffic": None, "peak_source": peak_src,
+                "note": "dominant kernel is FP64-pipe bound, not HBM bound (bit-faithful FP64 TSpectrum / FP64 LM); "
+                        "see stages and DESIGN.md",
+                "avg_launch_ms": stages[dom + "_ms"] / chunks / launches_per_chunk[dom]}
+    # fit-stage arithmetic: SURVEY §8(d) flops_iter(N) with the mean multiplicity
+    n_mean = pulses / max(1, fitted)
+    Pm = 1 + 2 * n_mean
+    flops_iter = 90 * (16 * n_mean + Pm * (Pm + 1) + 2 * Pm + 4) + Pm ** 3 / 3 + 2 * Pm ** 2
+    fit_gflops = (ctr["n_fit_iterations"] * flops_iter) / (stages["fit_ms"] * 1e-3) / 1e9 if stages["fit_ms"] > 0 else 0.0
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        import oracle
+        orc = oracle.Oracle(cal)
+        threads = os.cpu_count() or 1
+        probe = 2
+        sig = bufs[0][0][:256].cpu().numpy(); prs = bufs[0][1][:256].cpu().numpy(); cor = bufs[0][2][:256].cpu().numpy()
+        t0 = time.perf_counter()
+        orc.analyze_batch(sig[:probe], prs[:probe], cor[:probe], n_threads=threads)
+        per_ev = (time.perf_counter() - t0) / probe
+        n_s = int(max(threads, min(256, args.cpu_seconds / max(per_ev, 1e-6))))
+        n_s = min(256, max(probe, n_s))
+        t0 = time.perf_counter()
+        r = orc.analyze_batch(sig[:n_s], prs[:n_s], cor[:n_s], n_threads=threads)
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": float(((r["status"] & 28) > 0).sum()) / dt, "unit": UNIT, "cores": threads,
+                        "kind": "port", "seconds": dt,
+                        "sample": "first %d events of the resident batch (same workload), oracle with %d threads" % (n_s, threads)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic (generated on device, Philox-keyed by seed/event/block)",
+        "config": {"workload": workload_string(E, args.steps), "batch_events_per_gpu": E,
+                   "events_total": E * args.steps * world,
+                   "block_waveforms_per_s": blocks / (ms_total * 1e-3),
+                   "fitted_fraction": fitted / max(1, blocks), "mean_pulses_per_fit": n_mean,
+                   "fit_iterations_mean": iters / max(1, fitted), "fallback": n_fb, "retry_ok": n_retry,
+                   "l2": "inputs larger than L2: %.2f GB of traces per step, two resident batches alternated" % (E * NB * NT * 8 / 1e9)},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(chunks * 14),
+        "roofline": roofline, "stages": stage_rows,
+        "fit_fp64": {"gflops": fit_gflops, "flops_per_iter_model": flops_iter, "note": "SURVEY 8(d) flop model x measured iterations / fit-stage time"},
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -122,6 +122,13 @@ int npswf_analyze_batch_device(npswf_handle *h, int32_t dev_slot, int64_t n_even
  * (synchronises the slot's stream). */
 int npswf_sync_device(npswf_handle *h, int32_t dev_slot, void *stream);
 
+/* Per-stage device timing (CUDA events on the launching stream around front / search / fit of every
+ * chunk; replaces the TStopwatch prints of T2:1121-1124).  Times are folded in at the next
+ * npswf_sync_device / end of a host-buffer call.  ms_* are sums over n_chunks chunks. */
+int npswf_set_profiling(npswf_handle *h, int on);
+int npswf_get_stage_times(npswf_handle *h, double *ms_front, double *ms_search, double *ms_fit, int64_t *n_chunks,
+                          int reset);
+
 /* ---- stage-level batch entry points (host buffers), one per reference function ---- */
 
 /* FindPulsesMF (T2:124-216) for every present block of every event: matched filter, TSpectrum

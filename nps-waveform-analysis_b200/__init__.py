@@ -54,7 +54,8 @@ EXPORTS = [
     "npswf_analyze_batch_i16", "npswf_analyze_batch_device", "npswf_sync_device", "npswf_find_pulses_mf_batch",
     "npswf_pass_cluster_threshold_batch", "npswf_fitwf_batch", "npswf_matched_filter_batch",
     "npswf_tspectrum_debug", "npswf_get_mf_calib", "npswf_get_spline", "npswf_device_spline",
-    "npswf_device_timeref", "npswf_flatten_event", "npswf_debug_exp",
+    "npswf_device_timeref", "npswf_flatten_event", "npswf_debug_exp", "npswf_set_profiling",
+    "npswf_get_stage_times",
 ]
 
 _lib = None
@@ -205,6 +206,16 @@ class NpsWf:
         c = NpsWfCounters()
         self._check(lib().npswf_get_counters(self.h, C.byref(c)))
         return {n: getattr(c, n) for n, _ in NpsWfCounters._fields_}
+
+    def set_profiling(self, on=True):
+        self._check(lib().npswf_set_profiling(self.h, C.c_int(1 if on else 0)))
+
+    def stage_times(self, reset=True):
+        """Summed CUDA-event times (ms) of the front / search / fit stages and the chunk count."""
+        a, b, c, n = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+        self._check(lib().npswf_get_stage_times(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(n),
+                                                C.c_int(1 if reset else 0)))
+        return dict(front_ms=a.value, search_ms=b.value, fit_ms=c.value, chunks=n.value)
 
     def reset_counters(self):
         self._check(lib().npswf_reset_counters(self.h))

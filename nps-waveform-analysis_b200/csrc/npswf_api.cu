@@ -17,6 +17,7 @@
 #include "kernel_front.cuh"
 #include "kernel_search.cuh"
 #include "kernel_fit.cuh"
+#include "kernel_fit_small.cuh"
 
 using namespace npswf;
 
@@ -51,6 +52,9 @@ struct DevSlot {
     Workspace ws[2];
     DeviceCounters *ctr = nullptr;
     cudaStream_t own_stream = nullptr;
+    int occ_front = 2, occ_search = 4, occ_fit_big = 1, occ_fit_small[4] = {0, 4, 4, 2};  // resident CTAs per SM
+    std::vector<cudaEvent_t> prof_events;  // 4 per profiled chunk: start, after front, after search, after fits
+    std::vector<cudaEvent_t> prof_pool;
 };
 
 }  // namespace
@@ -65,6 +69,9 @@ struct npswf_handle {
     NpsWfCounters host_ctr{};
     int64_t chunk = 592;
     std::mutex mu;
+    bool profiling = false;
+    double stage_ms[3] = {0, 0, 0};  // front, search, fit
+    int64_t stage_chunks = 0;
 };
 
 namespace {
@@ -155,7 +162,7 @@ int alloc_workspace(npswf_handle *h, DevSlot &s, Workspace &w, int64_t cap, bool
     if ((rc = dev_alloc(h, s, &w.mf, nb * T))) return rc;
     if ((rc = dev_alloc(h, s, &w.minsig, nb))) return rc;
     if ((rc = dev_alloc(h, s, &w.flags, nb))) return rc;
-    if ((rc = dev_alloc(h, s, &w.fit_count, 16))) return rc;
+    if ((rc = dev_alloc(h, s, &w.fit_count, 32))) return rc;
     if ((rc = dev_alloc(h, s, &w.fit_list, (size_t)(MAXP + 1) * nb))) return rc;
     CU_TRY(h, cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
     return 0;
@@ -211,7 +218,7 @@ __global__ void build_jobs_kernel(const uint8_t *__restrict__ mask, const int32_
 int launch_front(npswf_handle *h, DevSlot &s, cudaStream_t st, const double *sig, const int32_t *pres, int64_t n,
                  float *mf, double *minsig, uint8_t *flags, int do_mf, int do_thr)
 {
-    const int grid = (int)std::min<int64_t>(n, (int64_t)s.sm_count * 2 * 4);
+    const int grid = (int)std::min<int64_t>(n, (int64_t)s.sm_count * s.occ_front);
     front_kernel<<<grid, FRONT_THREADS, FRONT_SMEM, st>>>(sig, pres, n, s.cal, h->kp, mf, minsig, flags, do_mf, do_thr);
     CU_TRY(h, cudaGetLastError());
     return 0;
@@ -224,13 +231,18 @@ int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, cons
     for (int N = 1; N <= MAXP; N++) {
         const int *list = w.fit_list + (size_t)N * stride;
         const int *cnt = w.fit_count + N;
-        if (N <= 3) {
-            const int grid = s.sm_count * 8;
-            fit_kernel<7><<<grid, FIT_THREADS, sizeof(FitSmem<7>) * FIT_WARPS, st>>>(
-                list, cnt, N, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr);
+        int *next = w.fit_count + 16 + N;  // per-multiplicity job cursor, zeroed with fit_count
+        if (N == 1) {
+            fit_small_kernel<1, 8, FS_MINB1><<<s.sm_count * s.occ_fit_small[1], FS_THREADS, 0, st>>>(
+                list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr);
+        } else if (N == 2) {
+            fit_small_kernel<2, 8, FS_MINB2><<<s.sm_count * s.occ_fit_small[2], FS_THREADS, 0, st>>>(
+                list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr);
+        } else if (N == 3) {
+            fit_small_kernel<3, 16, FS_MINB3><<<s.sm_count * s.occ_fit_small[3], FS_THREADS, 0, st>>>(
+                list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr);
         } else {
-            const int grid = s.sm_count * 2;
-            fit_kernel<25><<<grid, FIT_THREADS, sizeof(FitSmem<25>) * FIT_WARPS, st>>>(
+            fit_kernel<25><<<s.sm_count * s.occ_fit_big, FIT_THREADS, sizeof(FitSmem<25>) * FIT_WARPS, st>>>(
                 list, cnt, N, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr);
         }
         CU_TRY(h, cudaGetLastError());
@@ -243,16 +255,48 @@ int run_chunk(npswf_handle *h, DevSlot &s, Workspace &w, cudaStream_t st, int64_
               const int32_t *pres, const double *corr, int32_t *wfnpulse, double *wftime, double *wfampl, double *chi2,
               double *timewf, double *amplwf, uint8_t *status)
 {
-    CU_TRY(h, cudaMemsetAsync(w.fit_count, 0, 16 * sizeof(int), st));
+    CU_TRY(h, cudaMemsetAsync(w.fit_count, 0, 32 * sizeof(int), st));
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (h->profiling) {
+        for (int i = 0; i < 4; i++) {
+            if (!s.prof_pool.empty()) { ev[i] = s.prof_pool.back(); s.prof_pool.pop_back(); }
+            else CU_TRY(h, cudaEventCreate(&ev[i]));
+        }
+        CU_TRY(h, cudaEventRecord(ev[0], st));
+    }
     int rc = launch_front(h, s, st, sig, pres, n, w.mf, w.minsig, w.flags, 1, 1);
     if (rc) return rc;
+    if (h->profiling) CU_TRY(h, cudaEventRecord(ev[1], st));
     const long long items = (long long)n * B;
-    const int grid = (int)std::min<long long>((items + SEARCH_WARPS - 1) / SEARCH_WARPS, (long long)s.sm_count * 4 * 8);
+    const int grid = (int)std::min<long long>((items + SEARCH_WARPS - 1) / SEARCH_WARPS, (long long)s.sm_count * s.occ_search);
     search_kernel<<<grid, SEARCH_THREADS, SEARCH_SMEM, st>>>(w.mf, w.flags, w.minsig, sig, items, h->kp, wfnpulse, wftime,
                                                             wfampl, chi2, timewf, amplwf, status, w.fit_count,
                                                             w.fit_list, (long long)w.cap * B, s.ctr);
     CU_TRY(h, cudaGetLastError());
-    return launch_fits(h, s, st, w, sig, corr, wftime, wfampl, chi2, timewf, amplwf, status);
+    if (h->profiling) CU_TRY(h, cudaEventRecord(ev[2], st));
+    rc = launch_fits(h, s, st, w, sig, corr, wftime, wfampl, chi2, timewf, amplwf, status);
+    if (rc) return rc;
+    if (h->profiling) {
+        CU_TRY(h, cudaEventRecord(ev[3], st));
+        for (int i = 0; i < 4; i++) s.prof_events.push_back(ev[i]);
+    }
+    return 0;
+}
+
+// Resolve the recorded stage events of a slot (the stream must have been synchronised).
+int fold_profile(npswf_handle *h, DevSlot &s)
+{
+    for (size_t i = 0; i + 3 < s.prof_events.size(); i += 4) {
+        for (int k = 0; k < 3; k++) {
+            float ms = 0;
+            CU_TRY(h, cudaEventElapsedTime(&ms, s.prof_events[i + k], s.prof_events[i + k + 1]));
+            h->stage_ms[k] += ms;
+        }
+        h->stage_chunks++;
+        for (int k = 0; k < 4; k++) s.prof_pool.push_back(s.prof_events[i + k]);
+    }
+    s.prof_events.clear();
+    return 0;
 }
 
 template <class F>
@@ -323,7 +367,7 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
     }
     CU_TRY(h, cudaStreamSynchronize(s.ws[0].stream));
     CU_TRY(h, cudaStreamSynchronize(s.ws[1].stream));
-    return 0;
+    return fold_profile(h, s);
 }
 
 int check_handle(npswf_handle *h)
@@ -501,8 +545,18 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
         CR(cudaFuncSetAttribute(tspectrum_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEARCH_SMEM));
         CR(cudaFuncSetAttribute(fit_kernel<25>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(sizeof(FitSmem<25>) * FIT_WARPS)));
-        CR(cudaFuncSetAttribute(fit_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(sizeof(FitSmem<7>) * FIT_WARPS)));
+        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_front, front_kernel, FRONT_THREADS, FRONT_SMEM));
+        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_search, search_kernel, SEARCH_THREADS, SEARCH_SMEM));
+        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_big, fit_kernel<25>, FIT_THREADS,
+                                                         sizeof(FitSmem<25>) * FIT_WARPS));
+        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_small[1], fit_small_kernel<1, 8, FS_MINB1>, FS_THREADS, 0));
+        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_small[2], fit_small_kernel<2, 8, FS_MINB2>, FS_THREADS, 0));
+        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_small[3], fit_small_kernel<3, 16, FS_MINB3>, FS_THREADS, 0));
+        if (s.occ_front < 1 || s.occ_search < 1 || s.occ_fit_big < 1 || s.occ_fit_small[1] < 1 ||
+            s.occ_fit_small[2] < 1 || s.occ_fit_small[3] < 1) {
+            h->err = "a kernel does not fit on this device (occupancy 0)";
+            return fail(NPSWF_ERR_CUDA);
+        }
 #undef CR
     }
     *out = h;
@@ -518,6 +572,8 @@ void npswf_destroy(npswf_handle *h)
         for (int i = 0; i < 2; i++)
             if (s.ws[i].stream) cudaStreamDestroy(s.ws[i].stream);
         if (s.own_stream) cudaStreamDestroy(s.own_stream);
+        for (cudaEvent_t e : s.prof_events) cudaEventDestroy(e);
+        for (cudaEvent_t e : s.prof_pool) cudaEventDestroy(e);
         for (void *p : s.owned) cudaFree(p);
     }
     delete h;
@@ -641,6 +697,25 @@ int npswf_sync_device(npswf_handle *h, int32_t dev_slot, void *stream)
     DevSlot &s = h->slots[dev_slot];
     CU_TRY(h, cudaSetDevice(s.device));
     CU_TRY(h, cudaStreamSynchronize(stream ? (cudaStream_t)stream : s.own_stream));
+    return fold_profile(h, s);
+}
+
+int npswf_set_profiling(npswf_handle *h, int on)
+{
+    if (!h) return NPSWF_ERR_ARG;
+    h->profiling = on != 0;
+    return 0;
+}
+
+int npswf_get_stage_times(npswf_handle *h, double *ms_front, double *ms_search, double *ms_fit, int64_t *n_chunks,
+                          int reset)
+{
+    if (!h) return NPSWF_ERR_ARG;
+    if (ms_front) *ms_front = h->stage_ms[0];
+    if (ms_search) *ms_search = h->stage_ms[1];
+    if (ms_fit) *ms_fit = h->stage_ms[2];
+    if (n_chunks) *n_chunks = h->stage_chunks;
+    if (reset) { h->stage_ms[0] = h->stage_ms[1] = h->stage_ms[2] = 0; h->stage_chunks = 0; }
     return 0;
 }
 
@@ -749,7 +824,7 @@ int npswf_fitwf_batch(npswf_handle *h, int64_t n_events, const double *signal, c
         CU_TRY(h, cudaMemcpyAsync(w.wfnpulse, wfnpulse + ob, nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         CU_TRY(h, cudaMemcpyAsync(w.wftime, wftime + ob * MAXP, nb * MAXP * sizeof(double), cudaMemcpyHostToDevice, st));
         CU_TRY(h, cudaMemcpyAsync(w.wfampl, wfampl + ob * MAXP, nb * MAXP * sizeof(double), cudaMemcpyHostToDevice, st));
-        CU_TRY(h, cudaMemsetAsync(w.fit_count, 0, 16 * sizeof(int), st));
+        CU_TRY(h, cudaMemsetAsync(w.fit_count, 0, 32 * sizeof(int), st));
         build_jobs_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(w.mask, w.wfnpulse, (long long)nb, w.fit_count,
                                                                        w.fit_list, (long long)w.cap * B, w.chi2, w.status);
         CU_TRY(h, cudaGetLastError());

@@ -12,6 +12,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -324,7 +325,8 @@ LmResult lm_minimise(const WfChi2 &f, std::vector<double> &par, int max_iter, do
                 chi2 = c2;
                 lambda = std::max(lambda * 0.2, 1e-12);
                 accepted = true;
-                if (rel < 1e-12) converged = true;
+                static const double rel_tol = getenv("OR_LM_RELTOL") ? atof(getenv("OR_LM_RELTOL")) : 1e-9;  // same schedule as the CUDA fit kernels
+                if (rel < rel_tol) converged = true;
             } else {
                 lambda = std::max(lambda * 10, 1e-6);
             }
@@ -380,7 +382,8 @@ int fitwf_impl(const OracleHandle *h, int bn, const double *sig, int npulse, dou
     double fmin = 0;
     int ncalls = 0;
     if (h->cfg.flags & ORACLE_FLAG_FIT_LM) {
-        LmResult r = lm_minimise(f, par, 60, 1e-3);
+        static const double lam0 = getenv("OR_LM_LAMBDA0") ? atof(getenv("OR_LM_LAMBDA0")) : 1e-3;
+        LmResult r = lm_minimise(f, par, 60, lam0);
         ok = r.ok; fmin = r.chi2; ncalls = r.iters;
         if (ok) status = OR_ST_FIT_OK1;
         else {

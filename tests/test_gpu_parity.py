@@ -100,12 +100,12 @@ def test_cluster_threshold_off_lattice_and_near_threshold(gpu, orc):
     """Arbitrary doubles (sum order matters in the last bit) with 3x3 sums hovering around trig_thres."""
     rng = np.random.default_rng(11)
     sig = rng.normal(0.0, 0.4, (2, 1080, 110))
-    sig[:, :, 30:45] += rng.uniform(0.9, 1.3, (2, 1080, 1))     # 9 * ~1.1 ~ 10 mV in the window
+    sig[:, :, 30:45] += rng.uniform(0.55, 0.95, (2, 1080, 1))   # 9 * ~0.75 + noise max ~ 10 mV in the window
     pres = (rng.random((2, 1080)) > 0.1).astype(np.int32)
     ok = gpu.PassClusterThreshold(sig, pres)
     for e in range(2):
         ref = np.array([orc.pass_cluster_threshold(b, sig[e], pres[e]) for b in range(1080)])
-        assert 0.15 < ref.mean() < 0.85
+        assert 0.05 < ref.mean() < 0.95
         assert np.array_equal(ok[e], ref)
 
 
@@ -244,7 +244,8 @@ def test_device_entry_point_equals_host_entry_point(gpu, events):
              timewf=torch.empty((E, 1080), dtype=torch.float64, device=dev),
              amplwf=torch.empty((E, 1080), dtype=torch.float64, device=dev),
              status=torch.empty((E, 1080), dtype=torch.uint8, device=dev))
-    st = torch.cuda.current_stream().cuda_stream
+    stream = torch.cuda.Stream()
+    st = stream.cuda_stream
     gpu.analyze_device(E, sig.data_ptr(), pres.data_ptr(), corr.data_ptr(), o["wfnpulse"].data_ptr(),
                        o["wftime"].data_ptr(), o["wfampl"].data_ptr(), o["chi2"].data_ptr(), o["timewf"].data_ptr(),
                        o["amplwf"].data_ptr(), o["status"].data_ptr(), stream=st)

@@ -93,7 +93,9 @@ def main():
     sig = torch.empty((E, 1080, 110), dtype=torch.float64, device=dev)
     pres = torch.empty((E, 1080), dtype=torch.int32, device=dev)
     corr = torch.empty((E,), dtype=torch.float64, device=dev)
-    st = torch.cuda.current_stream().cuda_stream
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    st = stream.cuda_stream
     synth.generate_device(p, d_spl.data_ptr(), d_tref.data_ptr(), d_kap.data_ptr(), 0, E, sig.data_ptr(), 0,
                           pres.data_ptr(), corr.data_ptr(), st)
     torch.cuda.synchronize()
@@ -112,6 +114,7 @@ def main():
     for _ in range(2):
         run()
     torch.cuda.synchronize()
+    h.set_profiling(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(5):
@@ -119,6 +122,8 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
+    h.sync_device(stream=st)
+    print("stage times (5 steps):", h.stage_times())
     nfit = int(((o["status"] & 28) > 0).sum().item())
     print("resident cfg2: %d events %.2f ms/step -> %.3g block-wf/s, %.3g fitted/s (nfit %d, npulse hist %s)" % (
         E, ms, E * 1080 / ms * 1e3, nfit / ms * 1e3, nfit,
