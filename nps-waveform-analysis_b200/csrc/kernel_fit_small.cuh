@@ -130,6 +130,8 @@ __device__ __forceinline__ bool solve_damped(const NormalEq<P> &ne, double lambd
     return pd;
 }
 
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // 1 / Err[ib] with Err of T2:946-956: e = sqrt(|y*4.096/2|)/4.096, replaced by sqrt(2.048)/4.096 when
 // e < 1.  The comparison is exact: every operation in e(|y|) is a monotone rounded function, and
 // bisection on the rounded expression gives  e < 1  <=>  |y| < 0x1.0624dd2f1a9fcp+3 (= 8.192).
@@ -180,15 +182,32 @@ fit_small_kernel(const int *__restrict__ job_list, const int *__restrict__ job_c
 #pragma unroll
     for (int i = 0; i < P; i++) { par[i] = 0; seed[i] = 0; }
     cur.c2 = 0;
+    const unsigned group_mask = (GROUP == 32) ? FULL : (((1u << GROUP) - 1u) << leader);
+    int next_job = 0;
+    if (g == 0) next_job = atomicAdd(job_next, 1);
+    next_job = __shfl_sync(FULL, next_job, leader);
 
     for (;;) {
-        // ---- claim + load new jobs for idle groups
+        // ---- claim + load new jobs for idle groups.  Every group keeps one job claimed AHEAD of the one it
+        // is fitting and prefetches that job's trace into L1/L2 while it iterates, so the loads below hit
+        // cache instead of exposing HBM latency to the whole warp.
         const bool need = !has_job && !exhausted;
         if (__any_sync(FULL, need)) {
-            int j = 0;
-            if (need && g == 0) j = atomicAdd(job_next, 1);
-            j = __shfl_sync(FULL, j, leader);
+            int j2 = 0;
+            if (need && g == 0) j2 = atomicAdd(job_next, 1);
+            j2 = __shfl_sync(FULL, j2, leader);
             if (need) {
+                const int j = next_job;  // claimed one refill earlier (or the group's very first claim)
+                next_job = j2;
+                if (j2 < njobs) {
+                    const long long it2 = job_list[j2];
+                    const char *p2 = reinterpret_cast<const char *>(signal + (size_t)it2 * T);
+                    if (g * 128 < T * 8 + 127) prefetch_l1(p2 + g * 128);
+                    if (g == GROUP - 1) {
+                        prefetch_l1(wftime + (size_t)it2 * MAXP);
+                        prefetch_l1(wfampl + (size_t)it2 * MAXP);
+                    }
+                }
                 if (j < njobs) {
                     item = job_list[j];
                     bn = (int)(item % B);
@@ -201,8 +220,13 @@ fit_small_kernel(const int *__restrict__ job_list, const int *__restrict__ job_c
                         y[jj] = v;
                         w[jj] = (k < NFIT) ? inv_err(v) : 0.0;
                     }
-                    double ped = 0;  // T2:671-677
-                    for (int i = 0; i < 20; i++) ped = dadd(ped, sig[i]);
+                    // pedestal seed = mean of the first 20 samples (T2:671-677); summed as a tree inside the
+                    // group (a seed: its last bit does not matter for the tolerance-based fit outputs)
+                    double ped = 0;
+#pragma unroll
+                    for (int i = g; i < 20; i += GROUP) ped += sig[i];
+#pragma unroll
+                    for (int o = GROUP / 2; o > 0; o >>= 1) ped += __shfl_xor_sync(group_mask, ped, o);
                     seed[0] = ped / 20;
                     const double tref = cal.timeref[bn];
 #pragma unroll

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
+#include <cstdio>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -257,12 +258,15 @@ struct WfChi2 : ormn::FcnBase {
 // Independent minimiser of the same chi2 (analytic-Jacobian Levenberg-Marquardt), used
 // (a) with ORACLE_FLAG_FIT_LM as a fast CPU mode and (b) by tests to confirm Migrad's minima.
 struct LmResult { bool ok; double chi2; int iters; };
+std::atomic<long long> g_lm_tries{0}, g_lm_accepts{0}, g_lm_fits{0};
+struct LmStatsPrinter { ~LmStatsPrinter() { if (getenv("OR_LM_STATS")) fprintf(stderr, "LM stats: fits %lld tries %lld accepts %lld\n", g_lm_fits.load(), g_lm_tries.load(), g_lm_accepts.load()); } } g_lm_stats_printer;
 LmResult lm_minimise(const WfChi2 &f, std::vector<double> &par, int max_iter, double lambda0)
 {
     const int P = (int)par.size(), NP = OR_MFEND - OR_MFSTART;
     std::vector<double> JtJ((size_t)P * P), Jtr(P), J(P), A((size_t)P * P), dp(P), trial(P);
     double lambda = lambda0;
     double chi2 = f(par.data());
+    g_lm_fits++;
     bool converged = false;
     int it = 0;
     for (; it < max_iter; it++) {
@@ -319,10 +323,12 @@ LmResult lm_minimise(const WfChi2 &f, std::vector<double> &par, int max_iter, do
             }
             for (int a = 0; a < P; a++) trial[a] = par[a] + dp[a];
             double c2 = f(trial.data());
+            g_lm_tries++;
             if (c2 <= chi2) {
                 double rel = (chi2 - c2) / (std::fabs(chi2) + 1e-30);
                 par = trial;
                 chi2 = c2;
+                g_lm_accepts++;
                 lambda = std::max(lambda * 0.2, 1e-12);
                 accepted = true;
                 static const double rel_tol = getenv("OR_LM_RELTOL") ? atof(getenv("OR_LM_RELTOL")) : 1e-9;  // same schedule as the CUDA fit kernels
