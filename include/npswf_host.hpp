@@ -1,0 +1,106 @@
+// npswf_host.hpp — C++ host mirror of the reference's hot-path interface over the C ABI (npswf.h).
+//
+// The reference (/root/reference/TEST_2.C, "T2") calls analyze(event) once per RDataFrame row
+// (T2:1305).  Per-event synchronous calls defeat batching, so the drop-in replaces the
+// Define("tuple", analyze)...Snapshot section (T2:1305-1387) with: read + unpack a batch of events,
+// one call of npswf::Analyzer::analyze(), fill the WF tree.  Names and sentinels follow the
+// reference: wfnpulse, wftime/wfampl (flattened with blockOffset like T2:1294-1295), chi2 = -100,
+// timewf/amplwf = -100.  Header-only; link with -lnpswf.  No exceptions cross the C boundary; this
+// wrapper turns error codes into std::runtime_error for C++ callers.
+#ifndef NPSWF_HOST_HPP
+#define NPSWF_HOST_HPP
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "npswf.h"
+
+namespace npswf {
+
+struct EventResult {                      // what analyze() returns per event (T2:1289-1296)
+    std::vector<double> chi2, timewf, amplwf;   // [1080]
+    std::vector<int32_t> wfnpulse;              // [1080]
+    std::vector<double> wfampl, wftime;         // flattened: blocks with pulses only, block order
+    std::vector<int32_t> blockOffset;           // [1081]
+};
+
+class Analyzer {
+public:
+    Analyzer(const NpsWfConfig &cfg, const NpsWfCalib &calib)
+    {
+        if (int rc = npswf_create(&cfg, &calib, &h_)) throw std::runtime_error(std::string("npswf_create: ") + npswf_last_error(nullptr) + " (" + std::to_string(rc) + ")");
+    }
+    ~Analyzer() { npswf_destroy(h_); }
+    Analyzer(const Analyzer &) = delete;
+    Analyzer &operator=(const Analyzer &) = delete;
+
+    static NpsWfConfig defaults()
+    {
+        NpsWfConfig c;
+        npswf_default_config(&c);
+        return c;
+    }
+
+    // analyze() for n_events events.  signal: [E][1080][110] (the `signal` vector of T2:549 per event),
+    // pres: [E][1080] (T2:548), corr_time_HMS: [E] (T2:903).
+    std::vector<EventResult> analyze(int64_t n_events, const double *signal, const int32_t *pres,
+                                     const double *corr_time_HMS)
+    {
+        const size_t nb = (size_t)n_events * NPSWF_NBLOCKS;
+        std::vector<int32_t> n(nb);
+        std::vector<double> t(nb * NPSWF_MAXWFPULSES), a(nb * NPSWF_MAXWFPULSES), c(nb), tw(nb), aw(nb);
+        std::vector<uint8_t> st(nb);
+        check(npswf_analyze_batch(h_, n_events, signal, pres, corr_time_HMS, n.data(), t.data(), a.data(), c.data(),
+                                  tw.data(), aw.data(), st.data()));
+        std::vector<EventResult> out((size_t)n_events);
+        for (int64_t e = 0; e < n_events; e++) {
+            EventResult &r = out[(size_t)e];
+            const size_t o = (size_t)e * NPSWF_NBLOCKS;
+            r.chi2.assign(c.begin() + o, c.begin() + o + NPSWF_NBLOCKS);
+            r.timewf.assign(tw.begin() + o, tw.begin() + o + NPSWF_NBLOCKS);
+            r.amplwf.assign(aw.begin() + o, aw.begin() + o + NPSWF_NBLOCKS);
+            r.wfnpulse.assign(n.begin() + o, n.begin() + o + NPSWF_NBLOCKS);
+            r.blockOffset.resize(NPSWF_NBLOCKS + 1);
+            r.wftime.resize((size_t)NPSWF_NBLOCKS * NPSWF_MAXWFPULSES);
+            r.wfampl.resize((size_t)NPSWF_NBLOCKS * NPSWF_MAXWFPULSES);
+            const int64_t tot = npswf_flatten_event(&n[o], &t[o * NPSWF_MAXWFPULSES], &a[o * NPSWF_MAXWFPULSES],
+                                                    r.wftime.data(), r.wfampl.data(), r.blockOffset.data());
+            r.wftime.resize((size_t)tot);
+            r.wfampl.resize((size_t)tot);
+        }
+        return out;
+    }
+
+    // Stage-level mirrors (batched): FindPulsesMF (T2:124), PassClusterThreshold (T2:218), Fitwf (T2:601)
+    void FindPulsesMF(int64_t n_events, const double *signal, const int32_t *pres, int32_t *wfnpulse, double *wftime,
+                      double *wfampl)
+    {
+        check(npswf_find_pulses_mf_batch(h_, n_events, signal, pres, wfnpulse, wftime, wfampl));
+    }
+    void PassClusterThreshold(int64_t n_events, const double *signal, const int32_t *pres, uint8_t *ok)
+    {
+        check(npswf_pass_cluster_threshold_batch(h_, n_events, signal, pres, ok));
+    }
+    void Fitwf(int64_t n_events, const double *signal, const double *corr_time_HMS, const uint8_t *fit_mask,
+               const int32_t *wfnpulse, double *wftime, double *wfampl, double *chi2, uint8_t *status)
+    {
+        check(npswf_fitwf_batch(h_, n_events, signal, corr_time_HMS, fit_mask, wfnpulse, wftime, wfampl, chi2, status));
+    }
+    NpsWfCounters counters()
+    {
+        NpsWfCounters c;
+        check(npswf_get_counters(h_, &c));
+        return c;
+    }
+    npswf_handle *raw() { return h_; }
+
+private:
+    void check(int rc)
+    {
+        if (rc) throw std::runtime_error(std::string("npswf: ") + npswf_last_error(h_) + " (" + std::to_string(rc) + ")");
+    }
+    npswf_handle *h_ = nullptr;
+};
+
+}  // namespace npswf
+#endif
