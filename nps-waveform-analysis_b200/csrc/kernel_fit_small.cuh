@@ -130,7 +130,35 @@ __device__ __forceinline__ bool solve_damped(const NormalEq<P> &ne, double lambd
     return pd;
 }
 
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// cp.async (LDGSTS): global -> shared without staging registers; completion is awaited only at use time
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+constexpr int FS_STAGE_DOUBLES = 136;  // per group: 110 samples | wftime[12] | wfampl[12] (+2 pad)
+
+// stage C of the job pipeline: asynchronously copy the next job's trace and seeds into the group's
+// shared-memory staging buffer (880 B = 55 x 16 B, 16-byte aligned because 880 = 16 * 55)
+template <int N, int GROUP>
+__device__ __forceinline__ void stage_job(double *buf, long long item, int g, const double *__restrict__ signal,
+                                          const double *__restrict__ wftime, const double *__restrict__ wfampl)
+{
+    const double *src = signal + (size_t)item * T;
+#pragma unroll
+    for (int c = g; c < T / 2; c += GROUP) cp_async16(buf + 2 * c, src + 2 * c);
+    if (g < N) {
+        cp_async8(buf + T + g, wftime + (size_t)item * MAXP + g);
+        cp_async8(buf + T + MAXP + g, wfampl + (size_t)item * MAXP + g);
+    }
+    cp_async_commit();
+}
 
 // 1 / Err[ib] with Err of T2:946-956: e = sqrt(|y*4.096/2|)/4.096, replaced by sqrt(2.048)/4.096 when
 // e < 1.  The comparison is exact: every operation in e(|y|) is a monotone rounded function, and
@@ -183,40 +211,52 @@ fit_small_kernel(const int *__restrict__ job_list, const int *__restrict__ job_c
     for (int i = 0; i < P; i++) { par[i] = 0; seed[i] = 0; }
     cur.c2 = 0;
     const unsigned group_mask = (GROUP == 32) ? FULL : (((1u << GROUP) - 1u) << leader);
+    // first claim: resolved synchronously (once per kernel)
     int next_job = 0;
     if (g == 0) next_job = atomicAdd(job_next, 1);
     next_job = __shfl_sync(FULL, next_job, leader);
+    long long next_item = (next_job < njobs) ? (long long)job_list[next_job] : -1;
+    __shared__ __align__(16) double s_stage[(FS_THREADS / GROUP) * FS_STAGE_DOUBLES];
+    double *buf = s_stage + (threadIdx.x / GROUP) * FS_STAGE_DOUBLES;
+    if (next_item >= 0) stage_job<N, GROUP>(buf, next_item, g, signal, wftime, wfampl);
+    int stage = 0;  // 0: next_item staged; 1: next_job claimed, list read pending; 2: staging copy pending
 
     for (;;) {
-        // ---- claim + load new jobs for idle groups.  Every group keeps one job claimed AHEAD of the one it
-        // is fitting and prefetches that job's trace into L1/L2 while it iterates, so the loads below hit
-        // cache instead of exposing HBM latency to the whole warp.
+        // ---- job pipeline.  Every group keeps one job claimed AHEAD of the one it is fitting, and the three
+        // dependent memory round trips behind a claim (atomic cursor -> job list -> trace) are spread over
+        // three loop iterations, so none of them is waited for: stage A (at a refill) bumps the cursor,
+        // stage B (next iteration) reads the job list, stage C (the one after) prefetches the trace into L1.
+        if (stage == 2) {
+            if (next_item >= 0) stage_job<N, GROUP>(buf, next_item, g, signal, wftime, wfampl);
+            stage = 0;
+        }
+        if (stage == 1) {
+            next_item = (next_job < njobs) ? (long long)job_list[next_job] : -1;
+            stage = 2;
+        }
         const bool need = !has_job && !exhausted;
         if (__any_sync(FULL, need)) {
-            int j2 = 0;
-            if (need && g == 0) j2 = atomicAdd(job_next, 1);
-            j2 = __shfl_sync(FULL, j2, leader);
             if (need) {
-                const int j = next_job;  // claimed one refill earlier (or the group's very first claim)
-                next_job = j2;
-                if (j2 < njobs) {
-                    const long long it2 = job_list[j2];
-                    const char *p2 = reinterpret_cast<const char *>(signal + (size_t)it2 * T);
-                    if (g * 128 < T * 8 + 127) prefetch_l1(p2 + g * 128);
-                    if (g == GROUP - 1) {
-                        prefetch_l1(wftime + (size_t)it2 * MAXP);
-                        prefetch_l1(wfampl + (size_t)it2 * MAXP);
-                    }
+                if (stage == 1 || stage == 2) {  // the claim-ahead has not been resolved yet (very short fit)
+                    if (stage == 1) next_item = (next_job < njobs) ? (long long)job_list[next_job] : -1;
+                    if (next_item >= 0) stage_job<N, GROUP>(buf, next_item, g, signal, wftime, wfampl);
+                    stage = 0;
                 }
-                if (j < njobs) {
-                    item = job_list[j];
+                const long long it_now = next_item;
+                int j2 = 0;
+                if (g == 0) j2 = atomicAdd(job_next, 1);  // stage A: result first used next iteration
+                next_job = __shfl_sync(group_mask, j2, leader);
+                stage = 1;
+                if (it_now >= 0) {
+                    item = it_now;
                     bn = (int)(item % B);
-                    const double *sig = signal + (size_t)item * T;
                     spl4 = reinterpret_cast<const double4 *>(cal.spline) + (size_t)bn * (T - 1);
+                    cp_async_wait_all();
+                    __syncwarp(group_mask);  // every lane's copies have landed and are visible to the group
 #pragma unroll
                     for (int jj = 0; jj < PTS; jj++) {
                         const int k = g + GROUP * jj;
-                        const double v = (k < NFIT) ? sig[MFSTART + k] : 0.0;
+                        const double v = (k < NFIT) ? buf[MFSTART + k] : 0.0;
                         y[jj] = v;
                         w[jj] = (k < NFIT) ? inv_err(v) : 0.0;
                     }
@@ -224,18 +264,19 @@ fit_small_kernel(const int *__restrict__ job_list, const int *__restrict__ job_c
                     // group (a seed: its last bit does not matter for the tolerance-based fit outputs)
                     double ped = 0;
 #pragma unroll
-                    for (int i = g; i < 20; i += GROUP) ped += sig[i];
+                    for (int i = g; i < 20; i += GROUP) ped += buf[i];
 #pragma unroll
                     for (int o = GROUP / 2; o > 0; o >>= 1) ped += __shfl_xor_sync(group_mask, ped, o);
                     seed[0] = ped / 20;
                     const double tref = cal.timeref[bn];
 #pragma unroll
                     for (int n = 0; n < N; n++) {
-                        seed[1 + 2 * n] = dsub(wftime[(size_t)item * MAXP + n], tref);  // T2:662
-                        seed[2 + 2 * n] = wfampl[(size_t)item * MAXP + n];              // T2:663
+                        seed[1 + 2 * n] = dsub(buf[T + n], tref);   // wftime - timeref   T2:662
+                        seed[2 + 2 * n] = buf[T + MAXP + n];        // wfampl             T2:663
                     }
 #pragma unroll
                     for (int i = 0; i < P; i++) par[i] = seed[i];
+                    __syncwarp(group_mask);  // the buffer may be refilled from here on
                     has_job = true; fresh = true;
                     lambda = 1e-3; attempt = 1; max_iter = kp.fit_max_iter; iters = 0; it_total = 0; rejects = 0;
                 } else {
@@ -321,7 +362,7 @@ fit_small_kernel(const int *__restrict__ job_list, const int *__restrict__ job_c
                 }
                 if (timewf) timewf[item] = bt;
                 if (amplwf) amplwf[item] = ba;
-                if (status) status[item] |= (uint8_t)st;
+                if (status) status[item] = (uint8_t)(NPSWF_ST_PRESENT | NPSWF_ST_OKTOFIT | st);  // fit jobs are present && okToFit
                 c_it += it_total;
                 c_att++;
             }

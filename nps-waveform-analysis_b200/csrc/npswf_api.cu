@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -52,6 +53,7 @@ struct DevSlot {
     Workspace ws[2];
     DeviceCounters *ctr = nullptr;
     cudaStream_t own_stream = nullptr;
+    bool fit2_group16 = false;  // development knob (env NPSWF_FIT2_GROUP=16)
     int occ_front = 2, occ_search = 4, occ_fit_big = 1, occ_fit_small[4] = {0, 4, 4, 2};  // resident CTAs per SM
     std::vector<cudaEvent_t> prof_events;  // 4 per profiled chunk: start, after front, after search, after fits
     std::vector<cudaEvent_t> prof_pool;
@@ -234,6 +236,9 @@ int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, cons
         int *next = w.fit_count + 16 + N;  // per-multiplicity job cursor, zeroed with fit_count
         if (N == 1) {
             fit_small_kernel<1, 8, FS_MINB1><<<s.sm_count * s.occ_fit_small[1], FS_THREADS, 0, st>>>(
+                list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr);
+        } else if (N == 2 && s.fit2_group16) {
+            fit_small_kernel<2, 16, 3><<<s.sm_count * s.occ_fit_small[2], FS_THREADS, 0, st>>>(
                 list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr);
         } else if (N == 2) {
             fit_small_kernel<2, 8, FS_MINB2><<<s.sm_count * s.occ_fit_small[2], FS_THREADS, 0, st>>>(
@@ -550,7 +555,11 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_big, fit_kernel<25>, FIT_THREADS,
                                                          sizeof(FitSmem<25>) * FIT_WARPS));
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_small[1], fit_small_kernel<1, 8, FS_MINB1>, FS_THREADS, 0));
-        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_small[2], fit_small_kernel<2, 8, FS_MINB2>, FS_THREADS, 0));
+        s.fit2_group16 = getenv("NPSWF_FIT2_GROUP") && atoi(getenv("NPSWF_FIT2_GROUP")) == 16;
+        if (s.fit2_group16)
+            CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_small[2], fit_small_kernel<2, 16, 3>, FS_THREADS, 0));
+        else
+            CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_small[2], fit_small_kernel<2, 8, FS_MINB2>, FS_THREADS, 0));
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_small[3], fit_small_kernel<3, 16, FS_MINB3>, FS_THREADS, 0));
         if (s.occ_front < 1 || s.occ_search < 1 || s.occ_fit_big < 1 || s.occ_fit_small[1] < 1 ||
             s.occ_fit_small[2] < 1 || s.occ_fit_small[3] < 1) {

@@ -88,3 +88,15 @@ def test_synth_lattice_and_determinism(calib, spline):
     assert np.array_equal(a["signal"][1], b["signal"][0])               # keyed by (seed, event, block)
     assert np.array_equal(a["counts"] * synth.LSB, a["signal"])         # exact on the ADC lattice
     assert (a["signal"][a["pres"] == 0] == 0).all() and 0.05 < (a["pres"] == 0).mean() < 0.15
+
+
+def test_cpp_host_mirror_compiles_and_refuses_cpu(tmp_path, pkg):
+    """include/npswf_host.hpp (the C++ mirror a ROOT macro would include) builds against libnpswf.so."""
+    import subprocess
+    exe = str(tmp_path / "host_mirror_smoke")
+    libdir = os.path.dirname(pkg.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "host_mirror_smoke.cpp"), "-o", exe,
+                           "-L", libdir, "-lnpswf", "-Wl,-rpath," + libdir])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
