@@ -54,7 +54,7 @@ EXPORTS = [
     "npswf_analyze_batch_i16", "npswf_analyze_batch_device", "npswf_sync_device", "npswf_find_pulses_mf_batch",
     "npswf_pass_cluster_threshold_batch", "npswf_fitwf_batch", "npswf_matched_filter_batch",
     "npswf_tspectrum_debug", "npswf_get_mf_calib", "npswf_get_spline", "npswf_device_spline",
-    "npswf_device_timeref", "npswf_flatten_event", "npswf_debug_exp", "npswf_set_profiling",
+    "npswf_device_timeref", "npswf_flatten_event", "npswf_debug_exp", "npswf_debug_exact_ops", "npswf_set_profiling",
     "npswf_get_stage_times",
 ]
 
@@ -312,6 +312,12 @@ class NpsWf:
         y = np.zeros_like(xs)
         self._check(lib().npswf_debug_exp(self.h, C.c_int64(xs.size), _p(xs), _p(y)))
         return y
+
+    def debug_exact_ops(self, n_trials, seed=1):
+        """(mismatches of the b/sqrt(s) chain, mismatches of the a/b chain) vs IEEE div/sqrt on the device."""
+        mm = np.zeros(2, np.uint64)
+        self._check(lib().npswf_debug_exact_ops(self.h, C.c_int64(int(n_trials)), C.c_uint64(int(seed)), _p(mm)))
+        return int(mm[0]), int(mm[1])
 
 
 def shard_range(n_events, rank, world_size):

@@ -52,6 +52,7 @@ struct DevSlot {
     std::vector<void *> owned;
     Workspace ws[2];
     DeviceCounters *ctr = nullptr;
+    const double *gold1 = nullptr;  // [2][138] first-iteration Gold denominators and reciprocals
     cudaStream_t own_stream = nullptr;
     bool fit2_group16 = false;  // development knob (env NPSWF_FIT2_GROUP=16)
     int occ_front = 2, occ_search = 4, occ_fit_big = 1, occ_fit_small[4] = {0, 4, 4, 2};  // resident CTAs per SM
@@ -217,6 +218,19 @@ __global__ void build_jobs_kernel(const uint8_t *__restrict__ mask, const int32_
     }
 }
 
+// search kernel launch: persistent CTAs, 32 spectra per CTA batch
+int launch_search(npswf_handle *h, DevSlot &s, cudaStream_t st, SearchArgs &a)
+{
+    a.kp = h->kp;
+    a.gold1 = s.gold1;
+    const long long batches = (a.n_items + SRB - 1) / SRB;
+    const int grid = (int)std::min<long long>(batches, (long long)s.sm_count * s.occ_search);
+    if (grid <= 0) return 0;
+    search_kernel<<<grid, SEARCH_THREADS, SEARCH_SMEM, st>>>(a);
+    CU_TRY(h, cudaGetLastError());
+    return 0;
+}
+
 int launch_front(npswf_handle *h, DevSlot &s, cudaStream_t st, const double *sig, const int32_t *pres, int64_t n,
                  float *mf, double *minsig, uint8_t *flags, int do_mf, int do_thr)
 {
@@ -272,12 +286,12 @@ int run_chunk(npswf_handle *h, DevSlot &s, Workspace &w, cudaStream_t st, int64_
     int rc = launch_front(h, s, st, sig, pres, n, w.mf, w.minsig, w.flags, 1, 1);
     if (rc) return rc;
     if (h->profiling) CU_TRY(h, cudaEventRecord(ev[1], st));
-    const long long items = (long long)n * B;
-    const int grid = (int)std::min<long long>((items + SEARCH_WARPS - 1) / SEARCH_WARPS, (long long)s.sm_count * s.occ_search);
-    search_kernel<<<grid, SEARCH_THREADS, SEARCH_SMEM, st>>>(w.mf, w.flags, w.minsig, sig, items, h->kp, wfnpulse, wftime,
-                                                            wfampl, chi2, timewf, amplwf, status, w.fit_count,
-                                                            w.fit_list, (long long)w.cap * B, s.ctr);
-    CU_TRY(h, cudaGetLastError());
+    SearchArgs sa{};
+    sa.hist = w.mf; sa.flags = w.flags; sa.minsig = w.minsig; sa.signal = sig; sa.n_items = (long long)n * B;
+    sa.wfnpulse = wfnpulse; sa.wftime = wftime; sa.wfampl = wfampl; sa.chi2 = chi2; sa.timewf = timewf; sa.amplwf = amplwf;
+    sa.status = status; sa.fit_count = w.fit_count; sa.fit_list = w.fit_list; sa.fit_list_stride = (long long)w.cap * B;
+    sa.ctr = s.ctr;
+    if ((rc = launch_search(h, s, st, sa))) return rc;
     if (h->profiling) CU_TRY(h, cudaEventRecord(ev[2], st));
     rc = launch_fits(h, s, st, w, sig, corr, wftime, wfampl, chi2, timewf, amplwf, status);
     if (rc) return rc;
@@ -539,7 +553,17 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
         if ((rc = dev_upload(h, s, &s.cal.cortime, cal->cortime, (size_t)B))) return fail(rc);
         if ((rc = dev_upload(h, s, &s.cal.preswf, cal->preswf, (size_t)B))) return fail(rc);
         if ((rc = dev_upload(h, s, &s.cal.spline, h->spline.data(), h->spline.size()))) return fail(rc);
-        CR(cudaMemcpyToSymbol(c_ts_ata, ata, sizeof ata));
+        {   // Gold iteration 1 (x = 1): den[i] = sum of the in-range At*A taps (integers: exact), and RN(1/den[i])
+            std::vector<double> g1(2 * TS_S);
+            for (int i = 0; i < TS_S; i++) {
+                double den = 0;
+                for (int j = -(TS_LH - 1); j <= TS_LH - 1; j++)
+                    if (i + j >= 0 && i + j < TS_S) den = den + ata[j + TS_LH - 1] * 1.0;
+                g1[i] = den;
+                g1[TS_S + i] = 1.0 / den;
+            }
+            if ((rc = dev_upload(h, s, &s.gold1, g1.data(), g1.size()))) return fail(rc);
+        }
         if ((rc = dev_alloc(h, s, &s.ctr, 1))) return fail(rc);
         CR(cudaMemset(s.ctr, 0, sizeof(DeviceCounters)));
         CR(cudaStreamCreateWithFlags(&s.own_stream, cudaStreamNonBlocking));
@@ -547,7 +571,6 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
             if ((rc = alloc_workspace(h, s, s.ws[i], h->chunk, false))) return fail(rc);
         CR(cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRONT_SMEM));
         CR(cudaFuncSetAttribute(search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEARCH_SMEM));
-        CR(cudaFuncSetAttribute(tspectrum_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEARCH_SMEM));
         CR(cudaFuncSetAttribute(fit_kernel<25>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(sizeof(FitSmem<25>) * FIT_WARPS)));
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_front, front_kernel, FRONT_THREADS, FRONT_SMEM));
@@ -747,12 +770,10 @@ int npswf_find_pulses_mf_batch(npswf_handle *h, int64_t n_events, const double *
         CU_TRY(h, cudaMemcpyAsync(w.signal, signal + ob * T, nb * T * sizeof(double), cudaMemcpyHostToDevice, st));
         CU_TRY(h, cudaMemcpyAsync(w.pres, pres + ob, nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         if ((rc = launch_front(h, s, st, w.signal, w.pres, n, w.mf, w.minsig, w.flags, 1, 0))) return rc;
-        const long long items = (long long)nb;
-        const int grid = (int)std::min<long long>((items + SEARCH_WARPS - 1) / SEARCH_WARPS, (long long)s.sm_count * 32);
-        search_kernel<<<grid, SEARCH_THREADS, SEARCH_SMEM, st>>>(w.mf, w.flags, w.minsig, w.signal, items, h->kp, w.wfnpulse,
-                                                                w.wftime, w.wfampl, nullptr, nullptr, nullptr, nullptr,
-                                                                nullptr, nullptr, 0, nullptr);
-        CU_TRY(h, cudaGetLastError());
+        SearchArgs sa{};
+        sa.hist = w.mf; sa.flags = w.flags; sa.minsig = w.minsig; sa.signal = w.signal; sa.n_items = (long long)nb;
+        sa.wfnpulse = w.wfnpulse; sa.wftime = w.wftime; sa.wfampl = w.wfampl;
+        if ((rc = launch_search(h, s, st, sa))) return rc;
         CU_TRY(h, cudaMemcpyAsync(wfnpulse + ob, w.wfnpulse, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         CU_TRY(h, cudaMemcpyAsync(wftime + ob * MAXP, w.wftime, nb * MAXP * sizeof(double), cudaMemcpyDeviceToHost, st));
         CU_TRY(h, cudaMemcpyAsync(wfampl + ob * MAXP, w.wfampl, nb * MAXP * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -865,9 +886,9 @@ int npswf_tspectrum_debug(npswf_handle *h, int64_t n, const float *hist, int32_t
     CU_TRY(h, cudaMalloc(&d_s, (size_t)n * TS_S * sizeof(double)));
     CU_TRY(h, cudaMalloc(&d_d, (size_t)n * T * sizeof(double)));
     CU_TRY(h, cudaMemcpy(d_h, hist, (size_t)n * T * sizeof(float), cudaMemcpyHostToDevice));
-    const int grid = (int)std::min<long long>((n + SEARCH_WARPS - 1) / SEARCH_WARPS, (long long)s.sm_count * 32);
-    tspectrum_debug_kernel<<<grid, SEARCH_THREADS, SEARCH_SMEM>>>(d_h, n, 100.0 * h->kp.specthres, d_n, d_p, d_s, d_d);
-    CU_TRY(h, cudaGetLastError());
+    SearchArgs sa{};
+    sa.hist = d_h; sa.n_items = n; sa.npeaks_out = d_n; sa.pos_out = d_p; sa.smoothed_out = d_s; sa.decon_out = d_d;
+    if ((rc = launch_search(h, s, nullptr, sa))) return rc;
     CU_TRY(h, cudaDeviceSynchronize());
     if (npeaks) CU_TRY(h, cudaMemcpy(npeaks, d_n, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (pos_x) CU_TRY(h, cudaMemcpy(pos_x, d_p, (size_t)n * MAXP * sizeof(double), cudaMemcpyDeviceToHost));
@@ -892,6 +913,28 @@ int npswf_debug_exp(npswf_handle *h, int64_t n, const double *x, double *y)
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaMemcpy(y, dy, (size_t)n * 8, cudaMemcpyDeviceToHost));
     cudaFree(dx); cudaFree(dy);
+    return 0;
+}
+
+int npswf_debug_exact_ops(npswf_handle *h, int64_t n_trials, uint64_t seed, uint64_t mismatch[2])
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (n_trials <= 0 || !mismatch) return NPSWF_ERR_ARG;
+    DevSlot &s = h->slots[0];
+    CU_TRY(h, cudaSetDevice(s.device));
+    unsigned long long *d = nullptr;
+    CU_TRY(h, cudaMalloc(&d, 16));
+    CU_TRY(h, cudaMemset(d, 0, 16));
+    const int threads = 256, blocks = s.sm_count * 8;
+    const int per_thread = (int)std::min<int64_t>(1 << 20, (n_trials + (int64_t)threads * blocks - 1) / ((int64_t)threads * blocks));
+    exact_ops_check_kernel<<<blocks, threads>>>((unsigned long long)seed, per_thread, d);
+    CU_TRY(h, cudaGetLastError());
+    unsigned long long out[2] = {0, 0};
+    CU_TRY(h, cudaMemcpy(out, d, 16, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    mismatch[0] = out[0];
+    mismatch[1] = out[1];
     return 0;
 }
 

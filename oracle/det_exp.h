@@ -35,12 +35,17 @@ static inline double oracle_det_exp(double x)
     int k = (int)kd;                     /* exact: kd is integer-valued */
     double r = fma(kd, -DET_EXP_LN2HIN, x);
     r = fma(kd, -DET_EXP_LN2LON, r);
-    /* exp(r) - 1 = r + r^2 (1/2 + r (1/6 + r (1/24 + r/120))),  |r| <= ln2/256 */
-    double q = fma(r, 0x1.1111111111111p-7, 0x1.5555555555555p-5);
-    q = fma(r, q, 0x1.5555555555555p-3);
-    q = fma(r, q, 0.5);
+    /* exp(r) - 1 = C(r) + S(r), |r| <= ln2/256, split into the even part C = r^2 (1/2 + r^2/24) and the odd
+       part S = r + r (r^2 (1/6 + r^2/120)).  exp(-x) has kd -> -kd, r -> -r exactly, so C is shared and S
+       only changes sign: a GPU lane gets exp(q) and exp(-q) from one reduction and one set of polynomials,
+       and this single-argument definition returns the same bits for either of them. */
     double r2 = r * r;
-    double tmp = fma(r2, q, r);
+    double c = fma(r2, 0x1.5555555555555p-5, 0.5);
+    double cm1 = r2 * c;
+    double s1 = fma(r2, 0x1.1111111111111p-7, 0x1.5555555555555p-3);
+    double s2 = r2 * s1;
+    double sn = fma(r, s2, r);
+    double tmp = cm1 + sn;
     uint64_t sb = oracle_det_exp_tab[k & (DET_EXP_N - 1)] + ((uint64_t)(int64_t)(k >> 7) << 52);
     double scale;
     memcpy(&scale, &sb, sizeof scale);

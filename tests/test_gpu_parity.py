@@ -35,6 +35,11 @@ def test_det_exp_bit_exact(gpu):
     assert np.array_equal(gpu.debug_exp(x), oracle.det_exp(x))
 
 
+def test_inlined_div_sqrt_chains_match_ieee(gpu):
+    """The search kernel's branch-free division / square-root chains vs __ddiv_rn / __dsqrt_rn, 2e9 operand pairs."""
+    assert gpu.debug_exact_ops(2_000_000_000, seed=7) == (0, 0)
+
+
 @pytest.mark.parametrize("cfg", [1, 2, 3])
 def test_matched_filter_bit_exact(gpu, orc, events, cfg):
     ev = events[cfg]
