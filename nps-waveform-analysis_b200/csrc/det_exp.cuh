@@ -46,32 +46,20 @@ __device__ __forceinline__ double det_exp(double x, const unsigned long long *ta
     return __fma_rn(scale, tmp, scale);
 }
 
-// Constants of det_exp_pair held in registers for the whole kernel: a 64-bit literal operand costs two
-// UMOV issue slots every time it is used, and the Markov step evaluates ~400 pairs per spectrum.
+// Constants of the hot FP64 chains live in constant memory: a 64-bit literal operand costs two UMOV issue
+// slots every time it is used (the Markov step evaluates ~400 pairs per spectrum), a constant-bank operand
+// costs none.  (ptxas folds literals back in however they are written, so they must come from memory.)
 struct DetExpConsts {
-    double invln2n, nln2hin, nln2lon, c24, c120, c6;
+    double invln2n, nln2hin, nln2lon, c24, c120, c6, c0375;
 };
-__device__ __forceinline__ double pin_reg(double x)
-{
-    asm volatile("" : "+d"(x));
-    return x;
-}
-__device__ __forceinline__ DetExpConsts det_exp_consts()
-{
-    DetExpConsts c;
-    c.invln2n = pin_reg(DET_EXP_INVLN2N);
-    c.nln2hin = pin_reg(-DET_EXP_LN2HIN);
-    c.nln2lon = pin_reg(-DET_EXP_LN2LON);
-    c.c24 = pin_reg(0x1.5555555555555p-5);
-    c.c120 = pin_reg(0x1.1111111111111p-7);
-    c.c6 = pin_reg(0x1.5555555555555p-3);
-    return c;
-}
+__constant__ DetExpConsts c_det_exp = {DET_EXP_INVLN2N, -DET_EXP_LN2HIN, -DET_EXP_LN2LON, 0x1.5555555555555p-5,
+                                       0x1.1111111111111p-7, 0x1.5555555555555p-3, 0.375};
 
-// ep = det_exp(q), em = det_exp(-q), bit for bit.  Requires |q| <= 700 (the caller guards).
-__device__ __forceinline__ void det_exp_pair(double q, const unsigned long long *tab, const DetExpConsts &C, double &ep,
-                                             double &em)
+// ep = det_exp(q), em = det_exp(-q), bit for bit, for |q| <= 700 (the caller guards; outside that range the
+// result is meaningless but nothing traps).
+__device__ __forceinline__ void det_exp_pair(double q, const unsigned long long *tab, double &ep, double &em)
 {
+    const DetExpConsts &C = c_det_exp;
     const double shift = 0x1.8p52;
     const double z = __dmul_rn(C.invln2n, q);
     double kd = __dadd_rn(z, shift);
