@@ -101,6 +101,11 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
                  : "memory");
 }
 
+// Knot form of the natural cubic spline for the thread-per-fit kernel: 16 bytes per knot instead of 32 per
+// segment, padded with zeros so that a clamped trial time never needs an index check.
+constexpr int KN_LO = 128;
+constexpr int KN_LEN = 368;
+
 struct DeviceCounters {
     unsigned long long n_present, n_pass_threshold, n_fit_attempted, n_fit_ok_first, n_fit_ok_retry, n_fallback;
     unsigned long long n_pulses, n_peak_buffer_full, n_fit_iterations;
@@ -115,12 +120,14 @@ struct DevCalib {
     const float *cortime;    // [B]
     const int32_t *preswf;   // [B]
     const double *spline;    // [B][109][4] = y, b, c, d
+    const double2 *knots;    // [B][KN_LEN] = (y_i, c_i = y''_i / 2) at knot i - KN_LO, zero outside 0..109
 };
 
 struct KParams {
     double specthres, mfthres, trig_thres, dt, timerefacc;
     int coinc_width;
     int fit_max_iter, fit_retry_max_iter;
+    int fit_thread_tries;   // LM tries the thread-per-fit kernel runs before handing a fit to the sub-warp kernel
 };
 
 }  // namespace npswf

@@ -185,7 +185,7 @@ fit_small_kernel(const int *__restrict__ job_list, const int *__restrict__ job_c
                  const double *__restrict__ signal, const double *__restrict__ corr_time_HMS, DevCalib cal, KParams kp,
                  double *__restrict__ wftime, double *__restrict__ wfampl, double *__restrict__ chi2_out,
                  double *__restrict__ timewf, double *__restrict__ amplwf, uint8_t *__restrict__ status,
-                 DeviceCounters *__restrict__ ctr)
+                 DeviceCounters *__restrict__ ctr, const double *__restrict__ cont_state = nullptr)
 {
     constexpr int P = 2 * N + 1;
     constexpr int PTS = 96 / GROUP;
@@ -243,6 +243,7 @@ fit_small_kernel(const int *__restrict__ job_list, const int *__restrict__ job_c
                     stage = 0;
                 }
                 const long long it_now = next_item;
+                const int job_now = next_job;
                 int j2 = 0;
                 if (g == 0) j2 = atomicAdd(job_next, 1);  // stage A: result first used next iteration
                 next_job = __shfl_sync(group_mask, j2, leader);
@@ -279,6 +280,14 @@ fit_small_kernel(const int *__restrict__ job_list, const int *__restrict__ job_c
                     __syncwarp(group_mask);  // the buffer may be refilled from here on
                     has_job = true; fresh = true;
                     lambda = 1e-3; attempt = 1; max_iter = kp.fit_max_iter; iters = 0; it_total = 0; rejects = 0;
+                    if (cont_state) {   // continuation of a fit started by fit_thread_kernel: its parameters, damping, counters
+                        const double *cs = cont_state + (size_t)job_now * 8;
+#pragma unroll
+                        for (int i = 0; i < P; i++) par[i] = cs[i];
+                        lambda = cs[P];
+                        const int pk = (int)cs[P + 1];
+                        iters = pk >> 6; rejects = pk & 63;
+                    }
                 } else {
                     exhausted = true;
                 }

@@ -1,0 +1,343 @@
+// Thread-per-fit kernel for N = 1, 2 pulses (P = 3, 5 parameters): the bulk of the fits.
+//
+// Same objective / policy as kernel_fit.cuh and kernel_fit_small.cuh (Fitwf, T2:601-828): chi2 of
+// p0 + sum A_n S(x - t_n) over the 90 points x = 10..99, damped Gauss-Newton with analytic spline
+// derivatives, attempt -> retry from the same seeds -> fall back to the TSpectrum values.
+//
+// Mapping: ONE THREAD owns one fit.  Its 90 trace samples sit in shared memory, transposed
+// ([point][lane], leading dimension 33) so that the 32 fits of a warp read point j conflict-free; the
+// normal equations, the Cholesky factor and the LM state are plain registers.  No shuffles, no
+// redundant solves, no partial sums.  Because the knots of the reference shape are the integers
+// 0..109, every point of a pulse has the same fractional offset f = frac(10 - t): the spline is a
+// 4-term polynomial in f with coefficient quads read at consecutive indices, and the in-range test
+// 1 < x - t < 109 (T2:629) becomes an integer interval of point indices, computed once per try.
+// Lanes are persistent: a thread whose fit is finished takes the next job from the warp's queue (32 job
+// ids claimed with one atomic, traces prefetched into L2 on claim), and the warp copies that trace -- and
+// the per-point weights 1/Err -- into the thread's shared-memory column.
+// A thread's latency per LM try is ~30x that of a sub-warp group, so this kernel only runs the first
+// `fit_thread_tries` tries of the first attempt (97 % of the fits converge inside them); a fit that needs
+// more hands its state (parameters, damping, step counters) to a continuation list that
+// fit_small_kernel finishes, including the retry / fall-back policy.
+#pragma once
+#include "common.cuh"
+#include "kernel_fit_small.cuh"
+
+namespace npswf {
+
+constexpr int FT_WARPS = 3;
+constexpr int FT_THREADS = FT_WARPS * 32;
+constexpr int FT_LD = 33;
+constexpr int FT_WARP_BYTES = NFIT * FT_LD * (int)(sizeof(double) + sizeof(float));   // y (f64) + 1/err (f32)
+constexpr size_t FT_SMEM = (size_t)FT_WARPS * FT_WARP_BYTES;                            // 106 920 B -> 2 CTAs per SM
+constexpr int FT_CONT_STRIDE = 8;   // doubles per continuation record: par[P] | lambda | iters * 64 + rejects
+
+// chi2 and normal equations of one fit at parameters p, all 90 points, one thread.
+// kn points at knot 0 of the block's zero-padded knot array.  U points per loop body; the loads of the next
+// body are issued before the arithmetic of the current one.
+template <int N, int U>
+__device__ __forceinline__ void eval_thread(const double (&p)[2 * N + 1], const double *__restrict__ ycol,
+                                            const float *__restrict__ wcol, const double2 *__restrict__ kn,
+                                            NormalEq<2 * N + 1> &ne)
+{
+    constexpr int P = 2 * N + 1;
+    static_assert(NFIT % U == 0, "U must divide the number of fit points");
+    const double2 *kp[N];
+    double2 k0[N];
+    double wa[N], wb[N], wc[N], wd[N], dc[N], dd[N], nA[N];
+    int jlo[N];
+    unsigned span[N];
+#pragma unroll
+    for (int n = 0; n < N; n++) {
+        // d_j = (10 + j) - t = u + j;  knot index floor(d_j) = floor(u) + j, fraction f = u - floor(u)
+        double u = (double)MFSTART - p[1 + 2 * n];
+        u = fmin(fmax(u, -120.0), 120.0);   // a wild trial step stays inside the zero padding of the knot array
+        const double fl = floor(u);
+        const int i0 = (int)fl;
+        const double f = u - fl, g = 1.0 - f;
+        // S = g y0 + f y1 + ((g^3 - g) c0 + (f^3 - f) c1) / 3,  S' = y1 - y0 + ((1 - 3 g^2) c0 + (3 f^2 - 1) c1) / 3
+        wa[n] = g; wb[n] = f;
+        wc[n] = (g * g * g - g) * (1.0 / 3.0); wd[n] = (f * f * f - f) * (1.0 / 3.0);
+        dc[n] = (1.0 - 3.0 * g * g) * (1.0 / 3.0); dd[n] = (3.0 * f * f - 1.0) * (1.0 / 3.0);
+        nA[n] = -p[2 + 2 * n];
+        // 1 < u + j < 109  (T2:629)  <=>  jl <= j <= jh
+        int jl = (int)floor(1.0 - u) + 1, jh = (int)ceil((double)(T - 1) - u) - 1;
+        jl = max(jl, 0);
+        jh = min(jh, NFIT - 1);
+        if (jh < jl) { jl = 1 << 20; jh = jl; }
+        jlo[n] = jl; span[n] = (unsigned)(jh - jl);
+        kp[n] = kn + i0;
+        k0[n] = __ldg(kp[n]);
+    }
+#pragma unroll
+    for (int i = 0; i < P * (P + 1) / 2; i++) ne.H[i] = 0;
+#pragma unroll
+    for (int i = 0; i < P; i++) ne.g[i] = 0;
+    ne.c2 = 0;
+    const double p0 = p[0];
+    double yq[U];
+    float wq[U];
+    double2 kq[N][U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        yq[u] = ycol[u * FT_LD];
+        wq[u] = wcol[u * FT_LD];
+#pragma unroll
+        for (int n = 0; n < N; n++) kq[n][u] = __ldg(kp[n] + u + 1);
+    }
+#pragma unroll 1
+    for (int j0 = 0; j0 < NFIT; j0 += U) {
+        double yc[U];
+        float wf[U];
+        double2 kc[N][U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            yc[u] = yq[u]; wf[u] = wq[u];
+#pragma unroll
+            for (int n = 0; n < N; n++) kc[n][u] = kq[n][u];
+        }
+        if (j0 + U < NFIT) {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                yq[u] = ycol[(j0 + U + u) * FT_LD];
+                wq[u] = wcol[(j0 + U + u) * FT_LD];
+#pragma unroll
+                for (int n = 0; n < N; n++) kq[n][u] = __ldg(kp[n] + j0 + U + u + 1);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int j = j0 + u;
+            const double wk = (double)wf[u];
+            double r = (yc[u] - p0) * wk;
+            double J[P];
+            J[0] = wk;
+#pragma unroll
+            for (int n = 0; n < N; n++) {
+                const double2 k1 = kc[n][u];
+                const double wkm = ((unsigned)(j - jlo[n]) <= span[n]) ? wk : 0.0;   // in range: 1 < x - t < 109
+                const double s = fma(wd[n], k1.y, fma(wc[n], k0[n].y, fma(wb[n], k1.x, wa[n] * k0[n].x)));
+                const double ds = fma(dd[n], k1.y, fma(dc[n], k0[n].y, k1.x - k0[n].x));
+                k0[n] = k1;
+                J[2 + 2 * n] = s * wkm;
+                J[1 + 2 * n] = nA[n] * (ds * wkm);
+                r = fma(nA[n], J[2 + 2 * n], r);
+            }
+            ne.c2 = fma(r, r, ne.c2);
+#pragma unroll
+            for (int a = 0; a < P; a++) {
+                ne.g[a] = fma(J[a], r, ne.g[a]);
+#pragma unroll
+                for (int b = 0; b <= a; b++) ne.H[a * (a + 1) / 2 + b] = fma(J[a], J[b], ne.H[a * (a + 1) / 2 + b]);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <int N>
+__global__ void __launch_bounds__(FT_THREADS, 2)
+fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_count, int *__restrict__ job_next,
+                  const double *__restrict__ signal, const double *__restrict__ corr_time_HMS, DevCalib cal, KParams kp,
+                  double *__restrict__ wftime, double *__restrict__ wfampl, double *__restrict__ chi2_out,
+                  double *__restrict__ timewf, double *__restrict__ amplwf, uint8_t *__restrict__ status,
+                  DeviceCounters *__restrict__ ctr, int *__restrict__ cont_count, int *__restrict__ cont_list,
+                  double *__restrict__ cont_state)
+{
+    constexpr int P = 2 * N + 1;
+    constexpr int U = (N == 1) ? 6 : 3;
+    constexpr double REL_TOL = 1e-9;
+    const unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char ft_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *ywarp = reinterpret_cast<double *>(ft_smem + (size_t)warp * FT_WARP_BYTES);   // [90][33] samples
+    float *wwarp = reinterpret_cast<float *>(ywarp + NFIT * FT_LD);                       // [90][33] 1/err
+    const double *ycol = ywarp + lane;
+    const float *wcol = wwarp + lane;
+    const int njobs = *job_count;
+    const int max_tries = kp.fit_thread_tries;
+    unsigned long long c_ok1 = 0, c_it = 0, c_att = 0;
+
+    bool has_job = false, exhausted = false, fresh = false;
+    long long item = 0;
+    int bn = 0;
+    const double2 *kn = cal.knots + KN_LO;
+    double par[P];
+    NormalEq<P> cur;
+    double lambda = 1e-3;
+    int iters = 0, rejects = 0, tries = 0;
+#pragma unroll
+    for (int i = 0; i < P; i++) par[i] = 0;
+#pragma unroll
+    for (int i = 0; i < P * (P + 1) / 2; i++) cur.H[i] = 0;
+#pragma unroll
+    for (int i = 0; i < P; i++) cur.g[i] = 0;
+    cur.c2 = 0;
+
+    // warp job queue: lane i holds the i-th job id of the current batch of 32
+    int q_item = -1, qpos = 32;
+    bool drained = false;   // the cursor has passed the end of the list
+
+    for (;;) {
+        // ---- hand new jobs to the lanes without one (up to 4 traces in flight per round)
+        unsigned m = __ballot_sync(FULL, !has_job && !exhausted);
+        bool got = false;
+        double ped = 0;
+        while (m) {
+            int ls[4];
+            long long its[4];
+            double v[4][4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                ls[k] = -1; its[k] = -1;
+#pragma unroll
+                for (int c4 = 0; c4 < 4; c4++) v[k][c4] = 0;
+                if (m) {
+                    if (qpos == 32 && !drained) {   // claim the next 32 job ids, start pulling their traces into L2
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(job_next, 32);
+                        base = __shfl_sync(FULL, base, 0);
+                        const int j = base + lane;
+                        q_item = (j < njobs) ? job_list[j] : -1;
+                        qpos = 0;
+                        drained = base + 32 >= njobs;
+                        if (q_item >= 0) {
+                            const char *pt = reinterpret_cast<const char *>(signal + (size_t)q_item * T);
+#pragma unroll
+                            for (int c = 0; c < 7; c++) prefetch_l2(pt + 128 * c);
+                            prefetch_l2(pt + T * 8 - 8);
+                        }
+                    }
+                    const int l = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int it = (qpos < 32) ? __shfl_sync(FULL, q_item, qpos) : -1;
+                    if (qpos < 32) qpos++;
+                    ls[k] = l;
+                    its[k] = it;
+                    if (it >= 0) {
+                        const double *src = signal + (size_t)it * T;
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; c4++) {
+                            const int c = 32 * c4 + lane;
+                            if (c < T) v[k][c4] = src[c];
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (ls[k] >= 0) {   // warp-uniform
+                    // pedestal seed = mean of the first 20 samples (T2:671-677); a seed: its last bit does not matter
+                    const double sum = warp_sum(lane < 20 ? v[k][0] : 0.0);
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; c4++) {
+                        const int c = 32 * c4 + lane;
+                        if (c >= MFSTART && c < MFEND && its[k] >= 0) {
+                            ywarp[(c - MFSTART) * FT_LD + ls[k]] = v[k][c4];
+                            wwarp[(c - MFSTART) * FT_LD + ls[k]] = (float)inv_err(v[k][c4]);
+                        }
+                    }
+                    if (lane == ls[k]) {
+                        if (its[k] >= 0) { item = its[k]; ped = sum / 20; got = true; }
+                        else exhausted = true;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (got) {
+            bn = (int)(item % B);
+            kn = cal.knots + (size_t)bn * KN_LEN + KN_LO;
+            const double tref = cal.timeref[bn];
+            par[0] = ped;
+#pragma unroll
+            for (int n = 0; n < N; n++) {
+                par[1 + 2 * n] = dsub(wftime[(size_t)item * MAXP + n], tref);   // wftime - timeref   T2:662
+                par[2 + 2 * n] = wfampl[(size_t)item * MAXP + n];               // wfampl             T2:663
+            }
+            has_job = true; fresh = true;
+            lambda = 1e-3; iters = 0; rejects = 0; tries = 0;
+        }
+        if (!__any_sync(FULL, has_job)) break;
+
+        // ---- one LM try (or the first evaluation of a fresh fit)
+        double dp[P], trial[P];
+        const bool pd = fresh ? true : solve_damped<P>(cur, lambda, dp);
+#pragma unroll
+        for (int i = 0; i < P; i++) trial[i] = par[i] + ((pd && !fresh) ? dp[i] : 0.0);
+        NormalEq<P> nxt;
+        eval_thread<N, U>(trial, ycol, wcol, kn, nxt);
+        bool finished = false, handoff = false;
+        if (has_job) {
+            tries++;
+            if (fresh) {
+                cur = nxt;
+                fresh = false;
+            } else if (pd && nxt.c2 <= cur.c2) {
+                const double rel = (cur.c2 - nxt.c2) / (fabs(cur.c2) + 1e-30);
+#pragma unroll
+                for (int i = 0; i < P; i++) par[i] = trial[i];
+                cur = nxt;
+                lambda = fmax(lambda * 0.2, 1e-12);
+                rejects = 0;
+                iters++;
+                if (rel < REL_TOL) finished = true;
+                else if (iters >= kp.fit_max_iter) handoff = true;   // the retry policy lives in fit_small_kernel
+            } else {
+                lambda = fmax(lambda * 10, 1e-6);
+                rejects++;
+                if (rejects >= 30) { finished = true; iters++; }  // no descent step left
+            }
+            if (!finished && tries >= max_tries) handoff = true;
+        }
+        if (handoff) {   // continuation record: fit_small_kernel re-evaluates at par and carries on
+            const int idx = atomicAdd(cont_count, 1);
+            cont_list[idx] = (int)item;
+            double *cs = cont_state + (size_t)idx * FT_CONT_STRIDE;
+#pragma unroll
+            for (int i = 0; i < P; i++) cs[i] = par[i];
+            cs[P] = lambda;
+            cs[P + 1] = (double)(iters * 64 + rejects);
+            has_job = false;
+        }
+        // ---- write back converged fits (T2:796-827)
+        if (finished) {
+            const long long e = item / B;
+            const double corr = corr_time_HMS ? corr_time_HMS[e] : 0.0;
+            const double cort = (double)cal.cortime[bn];
+            const double accdt = dmul(kp.timerefacc, kp.dt);
+            double bt = 0, ba = 0;  // T2:999-1016
+#pragma unroll
+            for (int n = 0; n < N; n++) {
+                const double oa = par[2 + 2 * n];
+                const double ot = dsub(dsub(dadd(dmul(par[1 + 2 * n], kp.dt), corr), cort), accdt);
+                wftime[(size_t)item * MAXP + n] = ot;
+                wfampl[(size_t)item * MAXP + n] = oa;
+                if (n == 0 || fabs(ot) < fabs(bt)) { bt = ot; ba = oa; }
+            }
+            chi2_out[item] = cur.c2 / (double)(NFIT - P);
+            if (timewf) timewf[item] = bt;
+            if (amplwf) amplwf[item] = ba;
+            if (status) status[item] = (uint8_t)(NPSWF_ST_PRESENT | NPSWF_ST_OKTOFIT | NPSWF_ST_FIT_OK1);
+            c_ok1++;
+            c_it += iters;
+            c_att++;
+            has_job = false;
+        }
+    }
+    if (ctr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            c_att += __shfl_xor_sync(FULL, c_att, o);
+            c_ok1 += __shfl_xor_sync(FULL, c_ok1, o);
+            c_it += __shfl_xor_sync(FULL, c_it, o);
+        }
+        if (lane == 0) {
+            if (c_att) atomicAdd(&ctr->n_fit_attempted, c_att);
+            if (c_ok1) atomicAdd(&ctr->n_fit_ok_first, c_ok1);
+            if (c_it) atomicAdd(&ctr->n_fit_iterations, c_it);
+        }
+    }
+}
+
+}  // namespace npswf

@@ -19,6 +19,7 @@
 #include "kernel_search.cuh"
 #include "kernel_fit.cuh"
 #include "kernel_fit_small.cuh"
+#include "kernel_fit_thread.cuh"
 
 using namespace npswf;
 
@@ -39,8 +40,12 @@ struct Workspace {  // per (device, pipeline stage) buffers for up to `cap` even
     double *wftime = nullptr, *wfampl = nullptr, *chi2 = nullptr, *timewf = nullptr, *amplwf = nullptr;
     uint8_t *status = nullptr;
     uint8_t *mask = nullptr;
-    int *fit_count = nullptr;  // [13]
-    int *fit_list = nullptr;   // [13][cap*B]
+    int *fit_count = nullptr;     // [64]: jobs per multiplicity, [16 + N]: job cursors, [32 + N]: continuation counts, [48 + N]: their cursors
+    int *cont_list = nullptr;     // [2][cap*B] fits handed from fit_thread_kernel to fit_small_kernel (N = 1, 2)
+    double *cont_state = nullptr; // [2][cap*B][8] their LM state
+    int *bucket_count = nullptr;  // [13][B] jobs per (multiplicity, block)
+    int *fit_list = nullptr;      // [13][B][cap] bucketed item ids
+    int *fit_dense = nullptr;     // [13][cap*B] block-major dense job lists (what the fit kernels read)
     cudaStream_t stream = nullptr;
     bool io = false;  // has the signal/pres/output staging buffers (host-buffer API) or only scratch
 };
@@ -54,7 +59,12 @@ struct DevSlot {
     DeviceCounters *ctr = nullptr;
     const double *gold1 = nullptr;  // [2][138] first-iteration Gold denominators and reciprocals
     cudaStream_t own_stream = nullptr;
+    cudaStream_t fit_stream[4] = {nullptr, nullptr, nullptr, nullptr};  // N = 1 | N = 2 | N = 3 | N >= 4 run concurrently
+    cudaEvent_t fit_fork = nullptr, fit_join[4] = {nullptr, nullptr, nullptr, nullptr}, chunk_join[2] = {nullptr, nullptr};
+    bool fit_concurrent = true;  // env NPSWF_FIT_CONCURRENT=0 serialises the fit kernels on the caller's stream
     bool fit2_group16 = false;  // development knob (env NPSWF_FIT2_GROUP=16)
+    bool fit_thread = true;     // thread-per-fit kernels for N = 1, 2 (env NPSWF_FIT_THREAD=0 selects the sub-warp kernels)
+    int occ_fit_thread[3] = {0, 3, 3};
     int occ_front = 2, occ_search = 4, occ_fit_big = 1, occ_fit_small[4] = {0, 4, 4, 2};  // resident CTAs per SM
     std::vector<cudaEvent_t> prof_events;  // 4 per profiled chunk: start, after front, after search, after fits
     std::vector<cudaEvent_t> prof_pool;
@@ -165,8 +175,12 @@ int alloc_workspace(npswf_handle *h, DevSlot &s, Workspace &w, int64_t cap, bool
     if ((rc = dev_alloc(h, s, &w.mf, nb * T))) return rc;
     if ((rc = dev_alloc(h, s, &w.minsig, nb))) return rc;
     if ((rc = dev_alloc(h, s, &w.flags, nb))) return rc;
-    if ((rc = dev_alloc(h, s, &w.fit_count, 32))) return rc;
+    if ((rc = dev_alloc(h, s, &w.fit_count, 64))) return rc;
+    if ((rc = dev_alloc(h, s, &w.cont_list, (size_t)2 * nb))) return rc;
+    if ((rc = dev_alloc(h, s, &w.cont_state, (size_t)2 * nb * FT_CONT_STRIDE))) return rc;
+    if ((rc = dev_alloc(h, s, &w.bucket_count, (size_t)(MAXP + 1) * B))) return rc;
     if ((rc = dev_alloc(h, s, &w.fit_list, (size_t)(MAXP + 1) * nb))) return rc;
+    if ((rc = dev_alloc(h, s, &w.fit_dense, (size_t)(MAXP + 1) * nb))) return rc;
     CU_TRY(h, cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
     return 0;
 }
@@ -203,7 +217,7 @@ __global__ void widen_counts_kernel(const int16_t *__restrict__ c, double *__res
 
 // job lists from an explicit mask (npswf_fitwf_batch): one thread per (event, block)
 __global__ void build_jobs_kernel(const uint8_t *__restrict__ mask, const int32_t *__restrict__ wfnpulse, long long n_items,
-                                  int *__restrict__ fit_count, int *__restrict__ fit_list, long long stride,
+                                  int *__restrict__ bucket_count, int *__restrict__ bucket_list, int bucket_cap,
                                   double *__restrict__ chi2, uint8_t *__restrict__ status)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -213,9 +227,49 @@ __global__ void build_jobs_kernel(const uint8_t *__restrict__ mask, const int32_
     int n = wfnpulse[i];
     if (n > MAXP) n = MAXP;
     if (mask[i] && n > 0) {
-        const int idx = atomicAdd(&fit_count[n], 1);
-        fit_list[(size_t)n * stride + idx] = (int)i;
+        const int bucket = n * B + (int)(i % B);
+        const int idx = atomicAdd(&bucket_count[bucket], 1);
+        bucket_list[(size_t)bucket * bucket_cap + idx] = (int)i;
     }
+}
+
+// Buckets -> dense, exactly block-major job lists (one per multiplicity) + their lengths.  CTA (c, n) owns the
+// blocks [27c, 27c + 27) of multiplicity n + 1: offset = sum of the counts of the blocks before them.
+constexpr int FC_BLOCKS = 27;
+__global__ void __launch_bounds__(256)
+fit_compact_kernel(const int *__restrict__ bucket_count, const int *__restrict__ bucket_list, int bucket_cap,
+                   int *__restrict__ fit_count, int *__restrict__ fit_dense, long long dense_stride)
+{
+    const int n = blockIdx.y + 1;
+    const int b0 = blockIdx.x * FC_BLOCKS;
+    __shared__ int s_part[8];
+    int part = 0;
+    for (int b = threadIdx.x; b < b0; b += blockDim.x) part += bucket_count[n * B + b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+    __syncthreads();
+    int off = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) off += s_part[i];
+    const int base = off;
+    int *dst = fit_dense + (size_t)n * dense_stride;
+    for (int b = b0; b < b0 + FC_BLOCKS && b < B; b++) {
+        const int c = bucket_count[n * B + b];
+        const int *src = bucket_list + (size_t)(n * B + b) * bucket_cap;
+        for (int i = threadIdx.x; i < c; i += blockDim.x) dst[off + i] = src[i];
+        off += c;
+    }
+    if (threadIdx.x == 0 && off > base) atomicAdd(&fit_count[n], off - base);
+}
+
+int launch_compact(npswf_handle *h, cudaStream_t st, Workspace &w)
+{
+    fit_compact_kernel<<<dim3((B + FC_BLOCKS - 1) / FC_BLOCKS, MAXP), 256, 0, st>>>(w.bucket_count, w.fit_list, (int)w.cap,
+                                                                                     w.fit_count, w.fit_dense,
+                                                                                     (long long)w.cap * B);
+    CU_TRY(h, cudaGetLastError());
+    return 0;
 }
 
 // search kernel launch: persistent CTAs, 32 spectra per CTA batch
@@ -244,11 +298,38 @@ int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, cons
                 double *wftime, double *wfampl, double *chi2, double *timewf, double *amplwf, uint8_t *status)
 {
     const long long stride = (long long)w.cap * B;
+    // The per-multiplicity kernels are independent (disjoint jobs) and every one of them ends in a tail of a
+    // few long fits, so they run on four side streams forked from / joined to the caller's stream.
+    cudaStream_t caller = st;
+    const bool conc = s.fit_concurrent && !h->profiling;
+    if (conc) {
+        CU_TRY(h, cudaEventRecord(s.fit_fork, caller));
+        for (int i = 0; i < 4; i++) CU_TRY(h, cudaStreamWaitEvent(s.fit_stream[i], s.fit_fork, 0));
+    }
     for (int N = 1; N <= MAXP; N++) {
-        const int *list = w.fit_list + (size_t)N * stride;
+        if (conc) st = s.fit_stream[N <= 3 ? N - 1 : 3];
+        const int *list = w.fit_dense + (size_t)N * stride;
         const int *cnt = w.fit_count + N;
         int *next = w.fit_count + 16 + N;  // per-multiplicity job cursor, zeroed with fit_count
-        if (N == 1) {
+        if (N <= 2 && s.fit_thread) {
+            // thread-per-fit for the first tries of every fit, then the sub-warp kernel on the fits handed over
+            int *ccnt = w.fit_count + 32 + N, *cnext = w.fit_count + 48 + N;
+            int *clist = w.cont_list + (size_t)(N - 1) * stride;
+            double *cstate = w.cont_state + (size_t)(N - 1) * stride * FT_CONT_STRIDE;
+            if (N == 1) {
+                fit_thread_kernel<1><<<s.sm_count * s.occ_fit_thread[1], FT_THREADS, FT_SMEM, st>>>(
+                    list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, ccnt, clist, cstate);
+                CU_TRY(h, cudaGetLastError());
+                fit_small_kernel<1, 8, FS_MINB1><<<s.sm_count * s.occ_fit_small[1], FS_THREADS, 0, st>>>(
+                    clist, ccnt, cnext, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, cstate);
+            } else {
+                fit_thread_kernel<2><<<s.sm_count * s.occ_fit_thread[2], FT_THREADS, FT_SMEM, st>>>(
+                    list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, ccnt, clist, cstate);
+                CU_TRY(h, cudaGetLastError());
+                fit_small_kernel<2, 8, FS_MINB2><<<s.sm_count * s.occ_fit_small[2], FS_THREADS, 0, st>>>(
+                    clist, ccnt, cnext, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, cstate);
+            }
+        } else if (N == 1) {
             fit_small_kernel<1, 8, FS_MINB1><<<s.sm_count * s.occ_fit_small[1], FS_THREADS, 0, st>>>(
                 list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr);
         } else if (N == 2 && s.fit2_group16) {
@@ -266,6 +347,12 @@ int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, cons
         }
         CU_TRY(h, cudaGetLastError());
     }
+    if (conc) {
+        for (int i = 0; i < 4; i++) {
+            CU_TRY(h, cudaEventRecord(s.fit_join[i], s.fit_stream[i]));
+            CU_TRY(h, cudaStreamWaitEvent(caller, s.fit_join[i], 0));
+        }
+    }
     return 0;
 }
 
@@ -274,7 +361,8 @@ int run_chunk(npswf_handle *h, DevSlot &s, Workspace &w, cudaStream_t st, int64_
               const int32_t *pres, const double *corr, int32_t *wfnpulse, double *wftime, double *wfampl, double *chi2,
               double *timewf, double *amplwf, uint8_t *status)
 {
-    CU_TRY(h, cudaMemsetAsync(w.fit_count, 0, 32 * sizeof(int), st));
+    CU_TRY(h, cudaMemsetAsync(w.fit_count, 0, 64 * sizeof(int), st));
+    CU_TRY(h, cudaMemsetAsync(w.bucket_count, 0, (size_t)(MAXP + 1) * B * sizeof(int), st));
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     if (h->profiling) {
         for (int i = 0; i < 4; i++) {
@@ -289,9 +377,10 @@ int run_chunk(npswf_handle *h, DevSlot &s, Workspace &w, cudaStream_t st, int64_
     SearchArgs sa{};
     sa.hist = w.mf; sa.flags = w.flags; sa.minsig = w.minsig; sa.signal = sig; sa.n_items = (long long)n * B;
     sa.wfnpulse = wfnpulse; sa.wftime = wftime; sa.wfampl = wfampl; sa.chi2 = chi2; sa.timewf = timewf; sa.amplwf = amplwf;
-    sa.status = status; sa.fit_count = w.fit_count; sa.fit_list = w.fit_list; sa.fit_list_stride = (long long)w.cap * B;
+    sa.status = status; sa.bucket_count = w.bucket_count; sa.bucket_list = w.fit_list; sa.bucket_cap = (int)w.cap;
     sa.ctr = s.ctr;
     if ((rc = launch_search(h, s, st, sa))) return rc;
+    if ((rc = launch_compact(h, st, w))) return rc;
     if (h->profiling) CU_TRY(h, cudaEventRecord(ev[2], st));
     rc = launch_fits(h, s, st, w, sig, corr, wftime, wfampl, chi2, timewf, amplwf, status);
     if (rc) return rc;
@@ -452,6 +541,7 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
     h->kp.dt = cfg->dt; h->kp.timerefacc = cfg->timerefacc; h->kp.coinc_width = cfg->coinc_width;
     h->kp.fit_max_iter = cfg->fit_max_iter > 0 ? cfg->fit_max_iter : 60;
     h->kp.fit_retry_max_iter = cfg->fit_retry_max_iter > 0 ? cfg->fit_retry_max_iter : 300;
+    h->kp.fit_thread_tries = (getenv("NPSWF_FIT_THREAD_TRIES") && atoi(getenv("NPSWF_FIT_THREAD_TRIES")) > 0) ? atoi(getenv("NPSWF_FIT_THREAD_TRIES")) : 20;
     h->chunk = cfg->chunk_events > 0 ? cfg->chunk_events : 592;
     // ---- derived calibration on the host (T2:440-451 for mfyref/mfint; spline coefficients)
     h->mfyref.assign((size_t)B * MFW, 0.0);
@@ -553,6 +643,15 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
         if ((rc = dev_upload(h, s, &s.cal.cortime, cal->cortime, (size_t)B))) return fail(rc);
         if ((rc = dev_upload(h, s, &s.cal.preswf, cal->preswf, (size_t)B))) return fail(rc);
         if ((rc = dev_upload(h, s, &s.cal.spline, h->spline.data(), h->spline.size()))) return fail(rc);
+        {   // knot form (y_i, c_i), zero padded: S on [i, i+1] from the two knots (kernel_fit_thread.cuh)
+            std::vector<double2> kn((size_t)B * KN_LEN, make_double2(0.0, 0.0));
+            for (int b = 0; b < B; b++) {
+                const double *co = h->spline.data() + (size_t)b * (T - 1) * 4;
+                for (int i = 0; i < T - 1; i++) kn[(size_t)b * KN_LEN + KN_LO + i] = make_double2(co[4 * i], co[4 * i + 2]);
+                kn[(size_t)b * KN_LEN + KN_LO + T - 1] = make_double2(cal->interpY[(size_t)b * T + T - 1], 0.0);
+            }
+            if ((rc = dev_upload(h, s, &s.cal.knots, kn.data(), kn.size()))) return fail(rc);
+        }
         {   // Gold iteration 1 (x = 1): den[i] = sum of the in-range At*A taps (integers: exact), and RN(1/den[i])
             std::vector<double> g1(2 * TS_S);
             for (int i = 0; i < TS_S; i++) {
@@ -567,6 +666,13 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
         if ((rc = dev_alloc(h, s, &s.ctr, 1))) return fail(rc);
         CR(cudaMemset(s.ctr, 0, sizeof(DeviceCounters)));
         CR(cudaStreamCreateWithFlags(&s.own_stream, cudaStreamNonBlocking));
+        s.fit_concurrent = !(getenv("NPSWF_FIT_CONCURRENT") && atoi(getenv("NPSWF_FIT_CONCURRENT")) == 0);
+        CR(cudaEventCreateWithFlags(&s.fit_fork, cudaEventDisableTiming));
+        for (int i = 0; i < 2; i++) CR(cudaEventCreateWithFlags(&s.chunk_join[i], cudaEventDisableTiming));
+        for (int i = 0; i < 4; i++) {
+            CR(cudaStreamCreateWithFlags(&s.fit_stream[i], cudaStreamNonBlocking));
+            CR(cudaEventCreateWithFlags(&s.fit_join[i], cudaEventDisableTiming));
+        }
         for (int i = 0; i < 2; i++)
             if ((rc = alloc_workspace(h, s, s.ws[i], h->chunk, false))) return fail(rc);
         CR(cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRONT_SMEM));
@@ -578,6 +684,12 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_big, fit_kernel<25>, FIT_THREADS,
                                                          sizeof(FitSmem<25>) * FIT_WARPS));
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_small[1], fit_small_kernel<1, 8, FS_MINB1>, FS_THREADS, 0));
+        s.fit_thread = !(getenv("NPSWF_FIT_THREAD") && atoi(getenv("NPSWF_FIT_THREAD")) == 0);
+        CR(cudaFuncSetAttribute(fit_thread_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
+        CR(cudaFuncSetAttribute(fit_thread_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
+        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_thread[1], fit_thread_kernel<1>, FT_THREADS, FT_SMEM));
+        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_thread[2], fit_thread_kernel<2>, FT_THREADS, FT_SMEM));
+        if (s.occ_fit_thread[1] < 1 || s.occ_fit_thread[2] < 1) { h->err = "fit_thread_kernel does not fit on this device"; return fail(NPSWF_ERR_CUDA); }
         s.fit2_group16 = getenv("NPSWF_FIT2_GROUP") && atoi(getenv("NPSWF_FIT2_GROUP")) == 16;
         if (s.fit2_group16)
             CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_small[2], fit_small_kernel<2, 16, 3>, FS_THREADS, 0));
@@ -604,6 +716,13 @@ void npswf_destroy(npswf_handle *h)
         for (int i = 0; i < 2; i++)
             if (s.ws[i].stream) cudaStreamDestroy(s.ws[i].stream);
         if (s.own_stream) cudaStreamDestroy(s.own_stream);
+        for (int i = 0; i < 4; i++) {
+            if (s.fit_stream[i]) cudaStreamDestroy(s.fit_stream[i]);
+            if (s.fit_join[i]) cudaEventDestroy(s.fit_join[i]);
+        }
+        if (s.fit_fork) cudaEventDestroy(s.fit_fork);
+        for (int i = 0; i < 2; i++)
+            if (s.chunk_join[i]) cudaEventDestroy(s.chunk_join[i]);
         for (cudaEvent_t e : s.prof_events) cudaEventDestroy(e);
         for (cudaEvent_t e : s.prof_pool) cudaEventDestroy(e);
         for (void *p : s.owned) cudaFree(p);
@@ -707,14 +826,29 @@ int npswf_analyze_batch_device(npswf_handle *h, int32_t dev_slot, int64_t n_even
     DevSlot &s = h->slots[dev_slot];
     CU_TRY(h, cudaSetDevice(s.device));
     cudaStream_t st = stream ? (cudaStream_t)stream : s.own_stream;
-    Workspace &w = s.ws[0];
-    for (int64_t e0 = 0; e0 < n_events; e0 += w.cap) {
+    // Chunks alternate between the two workspaces, each on its own internal stream forked from / joined to the
+    // caller's stream: the front + search kernels of chunk k+1 fill the SMs the fit tails of chunk k leave idle.
+    // With stage profiling on everything is serialised on the caller's stream so that the stage times are clean.
+    const bool overlap = !h->profiling && n_events > s.ws[0].cap;
+    if (overlap) {
+        CU_TRY(h, cudaEventRecord(s.fit_fork, st));
+        for (int i = 0; i < 2; i++) CU_TRY(h, cudaStreamWaitEvent(s.ws[i].stream, s.fit_fork, 0));
+    }
+    int which = 0;
+    for (int64_t e0 = 0; e0 < n_events; e0 += s.ws[0].cap, which ^= 1) {
+        Workspace &w = s.ws[overlap ? which : 0];
         const int64_t n = std::min<int64_t>(w.cap, n_events - e0);
         const size_t ob = (size_t)e0 * B;
-        rc = run_chunk(h, s, w, st, n, d_signal + ob * T, d_pres + ob, d_corr ? d_corr + e0 : nullptr,
+        rc = run_chunk(h, s, w, overlap ? w.stream : st, n, d_signal + ob * T, d_pres + ob, d_corr ? d_corr + e0 : nullptr,
                        d_wfnpulse ? d_wfnpulse + ob : nullptr, d_wftime + ob * MAXP, d_wfampl + ob * MAXP, d_chi2 + ob,
                        d_timewf ? d_timewf + ob : nullptr, d_amplwf ? d_amplwf + ob : nullptr, d_status + ob);
         if (rc) return rc;
+    }
+    if (overlap) {
+        for (int i = 0; i < 2; i++) {
+            CU_TRY(h, cudaEventRecord(s.chunk_join[i], s.ws[i].stream));
+            CU_TRY(h, cudaStreamWaitEvent(st, s.chunk_join[i], 0));
+        }
     }
     h->host_ctr.n_events += n_events;
     h->host_ctr.n_block_waveforms += n_events * B;
@@ -854,9 +988,12 @@ int npswf_fitwf_batch(npswf_handle *h, int64_t n_events, const double *signal, c
         CU_TRY(h, cudaMemcpyAsync(w.wfnpulse, wfnpulse + ob, nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         CU_TRY(h, cudaMemcpyAsync(w.wftime, wftime + ob * MAXP, nb * MAXP * sizeof(double), cudaMemcpyHostToDevice, st));
         CU_TRY(h, cudaMemcpyAsync(w.wfampl, wfampl + ob * MAXP, nb * MAXP * sizeof(double), cudaMemcpyHostToDevice, st));
-        CU_TRY(h, cudaMemsetAsync(w.fit_count, 0, 32 * sizeof(int), st));
-        build_jobs_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(w.mask, w.wfnpulse, (long long)nb, w.fit_count,
-                                                                       w.fit_list, (long long)w.cap * B, w.chi2, w.status);
+        CU_TRY(h, cudaMemsetAsync(w.fit_count, 0, 64 * sizeof(int), st));
+        CU_TRY(h, cudaMemsetAsync(w.bucket_count, 0, (size_t)(MAXP + 1) * B * sizeof(int), st));
+        build_jobs_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(w.mask, w.wfnpulse, (long long)nb, w.bucket_count,
+                                                                       w.fit_list, (int)w.cap, w.chi2, w.status);
+        CU_TRY(h, cudaGetLastError());
+        if ((rc = launch_compact(h, st, w))) return rc;
         CU_TRY(h, cudaGetLastError());
         if ((rc = launch_fits(h, s, st, w, w.signal, w.corr, w.wftime, w.wfampl, w.chi2, nullptr, nullptr, w.status))) return rc;
         CU_TRY(h, cudaMemcpyAsync(wftime + ob * MAXP, w.wftime, nb * MAXP * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Minimal resident-data step for ncu: W warm-up + K timed steps of the full pipeline on one batch
-(config 2, generated on device).  Usage: python tools/profile_step.py [events] [steps] [config]"""
+(config 2, generated on device).  Usage: python tools/profile_step.py [events] [steps] [config] [chunk_events]"""
 import importlib
 import os
 import sys
@@ -17,8 +17,9 @@ def main():
     E = int(sys.argv[1]) if len(sys.argv) > 1 else 592
     K = int(sys.argv[2]) if len(sys.argv) > 2 else 2
     cfg = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+    chunk = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     cal = synth.make_calibration()
-    h = pkg.NpsWf(cal)
+    h = pkg.NpsWf(cal, chunk_events=chunk)
     dev = torch.device("cuda:0")
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
@@ -51,6 +52,17 @@ def main():
     h.sync_device(stream=st)
     t = h.stage_times()
     c = h.counters()
+    import time
+    h.set_profiling(False)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(K):
+        h.analyze_device(E, sig.data_ptr(), pres.data_ptr(), corr.data_ptr(), o["wfnpulse"].data_ptr(),
+                         o["wftime"].data_ptr(), o["wfampl"].data_ptr(), o["chi2"].data_ptr(), o["timewf"].data_ptr(),
+                         o["amplwf"].data_ptr(), o["status"].data_ptr(), stream=st)
+    h.sync_device(stream=st)
+    wall = (time.perf_counter() - t0) / K * 1e3
+    print("wall %.3f ms/step | " % wall, end="")
     print("events %d steps %d cfg %d: per step front %.3f search %.3f fit %.3f ms | fits %d iters/fit %.2f retry %d fb %d" % (
         E, K, cfg, t["front_ms"] / K, t["search_ms"] / K, t["fit_ms"] / K, c["n_fit_attempted"] // K,
         c["n_fit_iterations"] / max(1, c["n_fit_attempted"]), c["n_fit_ok_retry"], c["n_fallback"]))
