@@ -8,8 +8,10 @@ pipeline (matched filter -> TSpectrum search -> 3x3 cluster threshold -> templat
   value : whole-job fitted block-waveforms/s with inputs resident in HBM (device-timed, max over ranks)
   e2e   : the same metric through the reference-facing C-ABI call npswf_analyze_batch with pinned HOST
           buffers; H2D of the inputs and D2H of every output are inside the timed region
-  roofline / stages : per-kernel CUDA-event times taken inside the timed region (library profiling
-          hooks record events on the launching stream), algorithmic bytes per SURVEY.md §8(d)
+  roofline / stages : per-stage CUDA-event times (library profiling hooks record events on the launching
+          stream) from a second pass over the same batches inside this script: with the hooks on, the library
+          serialises its streams so that every stage is timed alone; the timed region of `value` runs with
+          the hooks off (fit kernels on side streams, chunks overlapped).  Algorithmic bytes per SURVEY.md §8(d)
   cpu_baseline : the CPU oracle (a port/restatement of the reference path — ROOT is not installable)
           on the box's host cores, on a bounded sample of the same workload
 
@@ -132,8 +134,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch-events", type=int, default=2368, help="events per step per GPU (multiple of 592)")
-    ap.add_argument("--e2e-events", type=int, default=1184, help="events per end-to-end step per GPU")
-    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--e2e-events", type=int, default=4736, help="events per end-to-end step per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--stage-steps", type=int, default=4, help="steps of the serialised stage-profiling pass")
     ap.add_argument("--ref-events", type=int, default=24, help="--impl reference: events per step")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -206,8 +209,7 @@ def main():
     torch.cuda.synchronize()
     h.sync_device(stream=st)
     h.reset_counters()
-    h.stage_times(reset=True)
-    h.set_profiling(True)
+    h.set_profiling(False)
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.25)
@@ -222,9 +224,7 @@ def main():
     barrier()
     clocks = sampler.stop()
     h.sync_device(stream=st)
-    h.set_profiling(False)
     ms_total = e0.elapsed_time(e1)
-    stages = h.stage_times(reset=True)
     ctr = h.counters()
     fitted_local = ctr["n_fit_attempted"]
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -237,6 +237,18 @@ def main():
     fitted, blocks, pulses, iters, n_fb, n_retry = [int(v) for v in cnt.tolist()]
     value = fitted / (ms_total * 1e-3)
 
+    # ---- stage pass: same batches, profiling hooks on (streams serialised, every stage timed alone)
+    h.reset_counters()
+    h.stage_times(reset=True)
+    h.set_profiling(True)
+    for i in range(args.stage_steps):
+        step(i)
+    h.sync_device(stream=st)
+    h.set_profiling(False)
+    stages = h.stage_times(reset=True)
+    sctr = h.counters()
+    fp64_peak = h.fp64_peak_gflops() if rank == 0 else 0.0
+
     # ---- end to end through npswf_analyze_batch: pinned host buffers, H2D + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
@@ -244,9 +256,12 @@ def main():
         hs = pkg.pinned_empty((Ee, NB, NT), np.float64)
         hp = pkg.pinned_empty((Ee, NB), np.int32)
         hc = pkg.pinned_empty((Ee,), np.float64)
-        hs[...] = bufs[0][0][:Ee].cpu().numpy()
-        hp[...] = bufs[0][1][:Ee].cpu().numpy()
-        hc[...] = bufs[0][2][:Ee].cpu().numpy()
+        for o0 in range(0, Ee, E):          # the same synthetic events as the resident batches
+            b = bufs[(o0 // E) % n_buf]
+            n = min(E, Ee - o0)
+            hs[o0:o0 + n] = b[0][:n].cpu().numpy()
+            hp[o0:o0 + n] = b[1][:n].cpu().numpy()
+            hc[o0:o0 + n] = b[2][:n].cpu().numpy()
         ho = h.alloc_outputs(Ee, pinned=True)
         h.analyze(hs, hp, hc, out=ho)          # warm-up (allocates the staging buffers)
         h.analyze(hs, hp, hc, out=ho)
@@ -280,36 +295,36 @@ def main():
     peaks, peak_src = _peaks()
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     chunks = max(1, stages["chunks"])
-    units_local = ctr["n_block_waveforms"]
-    nbar = ctr["n_pulses"] / max(1, ctr["n_present"])
-    fit_local = max(1, ctr["n_fit_attempted"])
+    units_local = sctr["n_block_waveforms"]
+    nbar = sctr["n_pulses"] / max(1, sctr["n_present"])
     # algorithmic bytes per block-waveform, SURVEY.md §8(d) (FP64 input ABI, s = 8)
     alg = {
         "front": 880.0 + 1.0,                  # matched filter + 3x3 threshold: each sample once, 1 flag byte
         "search": 440.0 + 4.0 + 16.0 * nbar,   # reads the float MF spectrum, writes wfnpulse + (t, A) per pulse
         "fit": 880.0 + 16.0 * nbar + 13.0 + 16.0 * nbar,  # per FITTED block: trace + seeds in, chi2/status/(t, A) out
     }
-    stage_units = {"front": units_local, "search": units_local, "fit": ctr["n_fit_attempted"]}
+    stage_units = {"front": units_local, "search": units_local, "fit": sctr["n_fit_attempted"]}
     stage_rows = {}
     for k in ("front", "search", "fit"):
         ms = stages[k + "_ms"]
         gbs = stage_units[k] * alg[k] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-        stage_rows[k] = {"ms_per_step": ms / args.steps, "share": ms / max(1e-9, sum(stages[s + "_ms"] for s in ("front", "search", "fit"))),
+        stage_rows[k] = {"ms_per_step": ms / args.stage_steps, "share": ms / max(1e-9, sum(stages[s + "_ms"] for s in ("front", "search", "fit"))),
                          "alg_bytes_per_unit": alg[k], "achieved_gbs": gbs, "frac_of_hbm": gbs / hbm,
                          "units_per_s": stage_units[k] / (ms * 1e-3) if ms > 0 else 0.0}
     dom = max(("front", "search", "fit"), key=lambda k: stages[k + "_ms"])
-    launches_per_chunk = {"front": 1, "search": 1, "fit": 12}
-    roofline = {"kernel": {"front": "front_kernel", "search": "search_kernel", "fit": "fit_kernel<7>/<25> (12 launches)"}[dom],
+    launches_per_chunk = {"front": 1, "search": 1, "fit": 14}
+    roofline = {"kernel": {"front": "front_kernel", "search": "search_kernel", "fit": "fit_thread_kernel<1,2> + fit_small_kernel + fit_kernel<25> (14 launches)"}[dom],
                 "bound": "hbm", "achieved": stage_rows[dom]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
                 "frac": stage_rows[dom]["achieved_gbs"] / hbm, "traffic": None, "peak_source": peak_src,
-                "note": "dominant kernel is FP64-pipe bound, not HBM bound (bit-faithful FP64 TSpectrum / FP64 LM); "
-                        "see stages and DESIGN.md",
+                "note": "dominant stage is FP64-pipe bound, not HBM bound (bit-faithful FP64 TSpectrum / FP64 LM); "
+                        "see stages, fp64_peak_gflops_measured and DESIGN.md",
+                "measured_in": "serialised stage pass of %d steps inside bench.py (CUDA events on the launching stream)" % args.stage_steps,
                 "avg_launch_ms": stages[dom + "_ms"] / chunks / launches_per_chunk[dom]}
     # fit-stage arithmetic: SURVEY §8(d) flops_iter(N) with the mean multiplicity
     n_mean = pulses / max(1, fitted)
     Pm = 1 + 2 * n_mean
     flops_iter = 90 * (16 * n_mean + Pm * (Pm + 1) + 2 * Pm + 4) + Pm ** 3 / 3 + 2 * Pm ** 2
-    fit_gflops = (ctr["n_fit_iterations"] * flops_iter) / (stages["fit_ms"] * 1e-3) / 1e9 if stages["fit_ms"] > 0 else 0.0
+    fit_gflops = (sctr["n_fit_iterations"] * flops_iter) / (stages["fit_ms"] * 1e-3) / 1e9 if stages["fit_ms"] > 0 else 0.0
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -340,9 +355,12 @@ def main():
                    "fitted_fraction": fitted / max(1, blocks), "mean_pulses_per_fit": n_mean,
                    "fit_iterations_mean": iters / max(1, fitted), "fallback": n_fb, "retry_ok": n_retry,
                    "l2": "inputs larger than L2: %.2f GB of traces per step, two resident batches alternated" % (E * NB * NT * 8 / 1e9)},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(chunks * 14),
+        "clocks": clocks, "e2e": e2e,
+        "gpu_launches": int(args.steps * ((E + h.chunk_events - 1) // h.chunk_events) * 18),
         "roofline": roofline, "stages": stage_rows,
-        "fit_fp64": {"gflops": fit_gflops, "flops_per_iter_model": flops_iter, "note": "SURVEY 8(d) flop model x measured iterations / fit-stage time"},
+        "fit_fp64": {"gflops": fit_gflops, "flops_per_iter_model": flops_iter, "fp64_peak_gflops_measured": fp64_peak,
+                     "frac_of_fp64_peak": fit_gflops / fp64_peak if fp64_peak > 0 else None,
+                     "note": "SURVEY 8(d) flop model x measured accepted iterations / fit-stage time; peak = FMA-chain microbenchmark on this GPU"},
         "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line), flush=True)

@@ -178,6 +178,10 @@ int npswf_debug_exp(npswf_handle *h, int64_t n, const double *x, double *y);
  * mismatch[0] = b / sqrt(s) chain, mismatch[1] = a / b chain.  Both must be 0. */
 int npswf_debug_exact_ops(npswf_handle *h, int64_t n_trials, uint64_t seed, uint64_t mismatch[2]);
 
+/* Measurement tap: FP64 FMA throughput of device 0 (GFLOP/s, FMA = 2 flop) from a register-resident chain
+ * microbenchmark -- the denominator of the FP64-bound stages (TSpectrum search, template fit). */
+int npswf_debug_fp64_peak(npswf_handle *h, double *gflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,7 +54,7 @@ EXPORTS = [
     "npswf_analyze_batch_i16", "npswf_analyze_batch_device", "npswf_sync_device", "npswf_find_pulses_mf_batch",
     "npswf_pass_cluster_threshold_batch", "npswf_fitwf_batch", "npswf_matched_filter_batch",
     "npswf_tspectrum_debug", "npswf_get_mf_calib", "npswf_get_spline", "npswf_device_spline",
-    "npswf_device_timeref", "npswf_flatten_event", "npswf_debug_exp", "npswf_debug_exact_ops", "npswf_set_profiling",
+    "npswf_device_timeref", "npswf_flatten_event", "npswf_debug_exp", "npswf_debug_exact_ops", "npswf_debug_fp64_peak", "npswf_set_profiling",
     "npswf_get_stage_times",
 ]
 
@@ -153,6 +153,7 @@ class NpsWf:
         cfg.specthres, cfg.mfthres, cfg.trig_thres = specthres, mfthres, trig_thres
         cfg.coinc_width, cfg.dt, cfg.timerefacc = coinc_width, dt, timerefacc
         cfg.chunk_events, cfg.fit_max_iter, cfg.fit_retry_max_iter = chunk_events, fit_max_iter, fit_retry_max_iter
+        self.chunk_events = chunk_events if chunk_events > 0 else 1184   # library default (events per chunk)
         self._dev = None
         if devices is not None:
             self._dev = (C.c_int32 * len(devices))(*devices)
@@ -312,6 +313,12 @@ class NpsWf:
         y = np.zeros_like(xs)
         self._check(lib().npswf_debug_exp(self.h, C.c_int64(xs.size), _p(xs), _p(y)))
         return y
+
+    def fp64_peak_gflops(self):
+        """Measured FP64 FMA throughput of device 0 (GFLOP/s)."""
+        g = C.c_double(0.0)
+        self._check(lib().npswf_debug_fp64_peak(self.h, C.byref(g)))
+        return float(g.value)
 
     def debug_exact_ops(self, n_trials, seed=1):
         """(mismatches of the b/sqrt(s) chain, mismatches of the a/b chain) vs IEEE div/sqrt on the device."""

@@ -4,8 +4,10 @@
 // p0 + sum A_n S(x - t_n) over the 90 points x = 10..99, damped Gauss-Newton with analytic spline
 // derivatives, attempt -> retry from the same seeds -> fall back to the TSpectrum values.
 //
-// Mapping: ONE THREAD owns one fit.  Its 90 trace samples sit in shared memory, transposed
-// ([point][lane], leading dimension 33) so that the 32 fits of a warp read point j conflict-free; the
+// Mapping: ONE THREAD owns one fit.  Its 90 trace samples and weights 1/Err sit in shared memory as float2,
+// transposed ([point][lane], leading dimension 33) so that the 32 fits of a warp read point j conflict-free
+// (ADC samples are multiples of 1000/4096 mV and therefore exact in binary32; a trace that is not exactly
+// representable is handed to the sub-warp kernel untouched, so nothing is ever rounded); the
 // normal equations, the Cholesky factor and the LM state are plain registers.  No shuffles, no
 // redundant solves, no partial sums.  Because the knots of the reference shape are the integers
 // 0..109, every point of a pulse has the same fractional offset f = frac(10 - t): the spline is a
@@ -27,20 +29,31 @@ namespace npswf {
 constexpr int FT_WARPS = 3;
 constexpr int FT_THREADS = FT_WARPS * 32;
 constexpr int FT_LD = 33;
-constexpr int FT_WARP_BYTES = NFIT * FT_LD * (int)(sizeof(double) + sizeof(float));   // y (f64) + 1/err (f32)
-constexpr size_t FT_SMEM = (size_t)FT_WARPS * FT_WARP_BYTES;                            // 106 920 B -> 2 CTAs per SM
+constexpr int FT_WARP_BYTES = NFIT * FT_LD * (int)sizeof(float2);   // (y, 1/err) per point
+constexpr size_t FT_SMEM = (size_t)FT_WARPS * FT_WARP_BYTES;         // 71 280 B -> 3 CTAs per SM
 constexpr int FT_CONT_STRIDE = 8;   // doubles per continuation record: par[P] | lambda | iters * 64 + rejects
+
+// 1 / Err (T2:946-956) as the binary32 weight the kernel stores: the same branch point as inv_err(), the
+// square root through the FP32 MUFU (relative error 2^-22, the storage format itself rounds at 2^-24; both
+// are far inside the chi2 tolerance of 1e-3)
+__device__ __forceinline__ float inv_err_f32(double v)
+{
+    const double a = fabs(v);
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)a));   // 1/sqrt(a)
+    const float wv = r * 0x1.6e5b7ep+1f;                             // 4.096 / sqrt(2.048 a) = (1/sqrt a) * 4.096/sqrt(2.048)
+    return (a < 0x1.0624dd2f1a9fcp+3) ? 0x1.6e5b7ep+1f : wv;
+}
 
 // chi2 and normal equations of one fit at parameters p, all 90 points, one thread.
 // kn points at knot 0 of the block's zero-padded knot array.  U points per loop body; the loads of the next
 // body are issued before the arithmetic of the current one.
 template <int N, int U>
-__device__ __forceinline__ void eval_thread(const double (&p)[2 * N + 1], const double *__restrict__ ycol,
-                                            const float *__restrict__ wcol, const double2 *__restrict__ kn,
-                                            NormalEq<2 * N + 1> &ne)
+__device__ __forceinline__ void eval_thread(const double (&p)[2 * N + 1], const float2 *__restrict__ ywcol,
+                                            const double2 *__restrict__ kn, NormalEq<2 * N + 1> &ne)
 {
     constexpr int P = 2 * N + 1;
-    static_assert(NFIT % U == 0, "U must divide the number of fit points");
+    static_assert(NFIT % (2 * U) == 0, "2 U must divide the number of fit points");
     const double2 *kp[N];
     double2 k0[N];
     double wa[N], wb[N], wc[N], wd[N], dc[N], dd[N], nA[N];
@@ -74,46 +87,28 @@ __device__ __forceinline__ void eval_thread(const double (&p)[2 * N + 1], const 
     for (int i = 0; i < P; i++) ne.g[i] = 0;
     ne.c2 = 0;
     const double p0 = p[0];
-    double yq[U];
-    float wq[U];
-    double2 kq[N][U];
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-        yq[u] = ycol[u * FT_LD];
-        wq[u] = wcol[u * FT_LD];
-#pragma unroll
-        for (int n = 0; n < N; n++) kq[n][u] = __ldg(kp[n] + u + 1);
-    }
-#pragma unroll 1
-    for (int j0 = 0; j0 < NFIT; j0 += U) {
-        double yc[U];
-        float wf[U];
-        double2 kc[N][U];
+    // two register buffers of U points each: while one is consumed the other is being loaded (no copies)
+    float2 ywA[U], ywB[U];
+    double2 kA[N][U], kB[N][U];
+    auto load = [&](int jb, float2 (&yw)[U], double2 (&kk)[N][U]) {
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            yc[u] = yq[u]; wf[u] = wq[u];
+            yw[u] = ywcol[(jb + u) * FT_LD];
 #pragma unroll
-            for (int n = 0; n < N; n++) kc[n][u] = kq[n][u];
+            for (int n = 0; n < N; n++) kk[n][u] = __ldg(kp[n] + jb + u + 1);
         }
-        if (j0 + U < NFIT) {
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                yq[u] = ycol[(j0 + U + u) * FT_LD];
-                wq[u] = wcol[(j0 + U + u) * FT_LD];
-#pragma unroll
-                for (int n = 0; n < N; n++) kq[n][u] = __ldg(kp[n] + j0 + U + u + 1);
-            }
-        }
+    };
+    auto consume = [&](int jb, const float2 (&yw)[U], const double2 (&kk)[N][U]) {
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const int j = j0 + u;
-            const double wk = (double)wf[u];
-            double r = (yc[u] - p0) * wk;
+            const int j = jb + u;
+            const double wk = (double)yw[u].y;
+            double r = ((double)yw[u].x - p0) * wk;
             double J[P];
             J[0] = wk;
 #pragma unroll
             for (int n = 0; n < N; n++) {
-                const double2 k1 = kc[n][u];
+                const double2 k1 = kk[n][u];
                 const double wkm = ((unsigned)(j - jlo[n]) <= span[n]) ? wk : 0.0;   // in range: 1 < x - t < 109
                 const double s = fma(wd[n], k1.y, fma(wc[n], k0[n].y, fma(wb[n], k1.x, wa[n] * k0[n].x)));
                 const double ds = fma(dd[n], k1.y, fma(dc[n], k0[n].y, k1.x - k0[n].x));
@@ -130,13 +125,21 @@ __device__ __forceinline__ void eval_thread(const double (&p)[2 * N + 1], const 
                 for (int b = 0; b <= a; b++) ne.H[a * (a + 1) / 2 + b] = fma(J[a], J[b], ne.H[a * (a + 1) / 2 + b]);
             }
         }
+    };
+    load(0, ywA, kA);
+#pragma unroll 1
+    for (int j0 = 0; j0 < NFIT; j0 += 2 * U) {
+        load(j0 + U, ywB, kB);
+        consume(j0, ywA, kA);
+        if (j0 + 2 * U < NFIT) load(j0 + 2 * U, ywA, kA);
+        consume(j0 + U, ywB, kB);
     }
 }
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int N>
-__global__ void __launch_bounds__(FT_THREADS, 2)
+__global__ void __launch_bounds__(FT_THREADS) __maxnreg__((N == 1) ? 224 : 255)
 fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_count, int *__restrict__ job_next,
                   const double *__restrict__ signal, const double *__restrict__ corr_time_HMS, DevCalib cal, KParams kp,
                   double *__restrict__ wftime, double *__restrict__ wfampl, double *__restrict__ chi2_out,
@@ -145,15 +148,13 @@ fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
                   double *__restrict__ cont_state)
 {
     constexpr int P = 2 * N + 1;
-    constexpr int U = (N == 1) ? 6 : 3;
+    constexpr int U = (N == 1) ? 5 : 3;
     constexpr double REL_TOL = 1e-9;
     const unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char ft_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *ywarp = reinterpret_cast<double *>(ft_smem + (size_t)warp * FT_WARP_BYTES);   // [90][33] samples
-    float *wwarp = reinterpret_cast<float *>(ywarp + NFIT * FT_LD);                       // [90][33] 1/err
-    const double *ycol = ywarp + lane;
-    const float *wcol = wwarp + lane;
+    float2 *ywwarp = reinterpret_cast<float2 *>(ft_smem + (size_t)warp * FT_WARP_BYTES);   // [90][33] (sample, 1/err)
+    const float2 *ywcol = ywwarp + lane;
     const int njobs = *job_count;
     const int max_tries = kp.fit_thread_tries;
     unsigned long long c_ok1 = 0, c_it = 0, c_att = 0;
@@ -180,8 +181,11 @@ fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
 
     for (;;) {
         // ---- hand new jobs to the lanes without one (up to 4 traces in flight per round)
+        // (a round costs a few hundred issue slots whatever the number of idle lanes, so it waits for four of them
+        // unless the warp has nothing else to do)
         unsigned m = __ballot_sync(FULL, !has_job && !exhausted);
-        bool got = false;
+        if (__popc(m) < 4 && __any_sync(FULL, has_job)) m = 0;
+        bool got = false, inexact = false;
         double ped = 0;
         while (m) {
             int ls[4];
@@ -229,16 +233,19 @@ fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
                 if (ls[k] >= 0) {   // warp-uniform
                     // pedestal seed = mean of the first 20 samples (T2:671-677); a seed: its last bit does not matter
                     const double sum = warp_sum(lane < 20 ? v[k][0] : 0.0);
+                    bool exact = true;
 #pragma unroll
                     for (int c4 = 0; c4 < 4; c4++) {
                         const int c = 32 * c4 + lane;
                         if (c >= MFSTART && c < MFEND && its[k] >= 0) {
-                            ywarp[(c - MFSTART) * FT_LD + ls[k]] = v[k][c4];
-                            wwarp[(c - MFSTART) * FT_LD + ls[k]] = (float)inv_err(v[k][c4]);
+                            const float yf = (float)v[k][c4];
+                            exact = exact && ((double)yf == v[k][c4]);
+                            ywwarp[(c - MFSTART) * FT_LD + ls[k]] = make_float2(yf, inv_err_f32(v[k][c4]));
                         }
                     }
+                    exact = __all_sync(FULL, exact);
                     if (lane == ls[k]) {
-                        if (its[k] >= 0) { item = its[k]; ped = sum / 20; got = true; }
+                        if (its[k] >= 0) { item = its[k]; ped = sum / 20; got = true; inexact = !exact; }
                         else exhausted = true;
                     }
                 }
@@ -256,7 +263,8 @@ fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
                 par[2 + 2 * n] = wfampl[(size_t)item * MAXP + n];               // wfampl             T2:663
             }
             has_job = true; fresh = true;
-            lambda = 1e-3; iters = 0; rejects = 0; tries = 0;
+            lambda = 1e-3; iters = 0; rejects = 0;
+            tries = inexact ? (1 << 20) : 0;   // samples not exact in binary32: hand the fit over after the seed evaluation
         }
         if (!__any_sync(FULL, has_job)) break;
 
@@ -266,7 +274,7 @@ fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
 #pragma unroll
         for (int i = 0; i < P; i++) trial[i] = par[i] + ((pd && !fresh) ? dp[i] : 0.0);
         NormalEq<P> nxt;
-        eval_thread<N, U>(trial, ycol, wcol, kn, nxt);
+        eval_thread<N, U>(trial, ywcol, kn, nxt);
         bool finished = false, handoff = false;
         if (has_job) {
             tries++;

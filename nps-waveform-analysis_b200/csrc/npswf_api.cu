@@ -61,10 +61,12 @@ struct DevSlot {
     cudaStream_t own_stream = nullptr;
     cudaStream_t fit_stream[4] = {nullptr, nullptr, nullptr, nullptr};  // N = 1 | N = 2 | N = 3 | N >= 4 run concurrently
     cudaEvent_t fit_fork = nullptr, fit_join[4] = {nullptr, nullptr, nullptr, nullptr}, chunk_join[2] = {nullptr, nullptr};
+    int cont_group = 16;  // lanes per fit of the continuation kernels (env NPSWF_CONT_GROUP)
     bool fit_concurrent = true;  // env NPSWF_FIT_CONCURRENT=0 serialises the fit kernels on the caller's stream
     bool fit2_group16 = false;  // development knob (env NPSWF_FIT2_GROUP=16)
     bool fit_thread = true;     // thread-per-fit kernels for N = 1, 2 (env NPSWF_FIT_THREAD=0 selects the sub-warp kernels)
     int occ_fit_thread[3] = {0, 3, 3};
+    int fit_thread_maxocc = 0;  // env NPSWF_FIT_THREAD_OCC: cap on resident CTAs per SM (fewer CTAs leave more L1)
     int occ_front = 2, occ_search = 4, occ_fit_big = 1, occ_fit_small[4] = {0, 4, 4, 2};  // resident CTAs per SM
     std::vector<cudaEvent_t> prof_events;  // 4 per profiled chunk: start, after front, after search, after fits
     std::vector<cudaEvent_t> prof_pool;
@@ -80,7 +82,7 @@ struct npswf_handle {
     std::vector<double> mfyref, mfint, spline, timeref;
     std::string err;
     NpsWfCounters host_ctr{};
-    int64_t chunk = 592;
+    int64_t chunk = 1184;  // events per chunk (8 x 148 SMs): large enough to amortise the fit kernels' tails
     std::mutex mu;
     bool profiling = false;
     double stage_ms[3] = {0, 0, 0};  // front, search, fit
@@ -320,12 +322,26 @@ int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, cons
                 fit_thread_kernel<1><<<s.sm_count * s.occ_fit_thread[1], FT_THREADS, FT_SMEM, st>>>(
                     list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, ccnt, clist, cstate);
                 CU_TRY(h, cudaGetLastError());
+                if (s.cont_group == 32)
+                    fit_small_kernel<1, 32, 3><<<s.sm_count * 3, FS_THREADS, 0, st>>>(
+                        clist, ccnt, cnext, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, cstate);
+                else if (s.cont_group == 16)
+                    fit_small_kernel<1, 16, 3><<<s.sm_count * 3, FS_THREADS, 0, st>>>(
+                        clist, ccnt, cnext, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, cstate);
+                else
                 fit_small_kernel<1, 8, FS_MINB1><<<s.sm_count * s.occ_fit_small[1], FS_THREADS, 0, st>>>(
                     clist, ccnt, cnext, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, cstate);
             } else {
                 fit_thread_kernel<2><<<s.sm_count * s.occ_fit_thread[2], FT_THREADS, FT_SMEM, st>>>(
                     list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, ccnt, clist, cstate);
                 CU_TRY(h, cudaGetLastError());
+                if (s.cont_group == 32)
+                    fit_small_kernel<2, 32, 3><<<s.sm_count * 3, FS_THREADS, 0, st>>>(
+                        clist, ccnt, cnext, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, cstate);
+                else if (s.cont_group == 16)
+                    fit_small_kernel<2, 16, 3><<<s.sm_count * 3, FS_THREADS, 0, st>>>(
+                        clist, ccnt, cnext, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, cstate);
+                else
                 fit_small_kernel<2, 8, FS_MINB2><<<s.sm_count * s.occ_fit_small[2], FS_THREADS, 0, st>>>(
                     clist, ccnt, cnext, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, cstate);
             }
@@ -542,7 +558,7 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
     h->kp.fit_max_iter = cfg->fit_max_iter > 0 ? cfg->fit_max_iter : 60;
     h->kp.fit_retry_max_iter = cfg->fit_retry_max_iter > 0 ? cfg->fit_retry_max_iter : 300;
     h->kp.fit_thread_tries = (getenv("NPSWF_FIT_THREAD_TRIES") && atoi(getenv("NPSWF_FIT_THREAD_TRIES")) > 0) ? atoi(getenv("NPSWF_FIT_THREAD_TRIES")) : 20;
-    h->chunk = cfg->chunk_events > 0 ? cfg->chunk_events : 592;
+    h->chunk = cfg->chunk_events > 0 ? cfg->chunk_events : 1184;
     // ---- derived calibration on the host (T2:440-451 for mfyref/mfint; spline coefficients)
     h->mfyref.assign((size_t)B * MFW, 0.0);
     h->mfint.assign(B, 0.0);
@@ -666,6 +682,7 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
         if ((rc = dev_alloc(h, s, &s.ctr, 1))) return fail(rc);
         CR(cudaMemset(s.ctr, 0, sizeof(DeviceCounters)));
         CR(cudaStreamCreateWithFlags(&s.own_stream, cudaStreamNonBlocking));
+        if (getenv("NPSWF_CONT_GROUP")) s.cont_group = atoi(getenv("NPSWF_CONT_GROUP"));
         s.fit_concurrent = !(getenv("NPSWF_FIT_CONCURRENT") && atoi(getenv("NPSWF_FIT_CONCURRENT")) == 0);
         CR(cudaEventCreateWithFlags(&s.fit_fork, cudaEventDisableTiming));
         for (int i = 0; i < 2; i++) CR(cudaEventCreateWithFlags(&s.chunk_join[i], cudaEventDisableTiming));
@@ -689,6 +706,13 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
         CR(cudaFuncSetAttribute(fit_thread_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_thread[1], fit_thread_kernel<1>, FT_THREADS, FT_SMEM));
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_thread[2], fit_thread_kernel<2>, FT_THREADS, FT_SMEM));
+        if (getenv("NPSWF_FIT_THREAD_OCC")) s.fit_thread_maxocc = atoi(getenv("NPSWF_FIT_THREAD_OCC"));
+        if (s.fit_thread_maxocc > 0) {
+            for (int n = 1; n <= 2; n++) s.occ_fit_thread[n] = std::min(s.occ_fit_thread[n], s.fit_thread_maxocc);
+            const int carve = (int)((s.fit_thread_maxocc * (FT_SMEM + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+            CR(cudaFuncSetAttribute(fit_thread_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(100, carve)));
+            CR(cudaFuncSetAttribute(fit_thread_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(100, carve)));
+        }
         if (s.occ_fit_thread[1] < 1 || s.occ_fit_thread[2] < 1) { h->err = "fit_thread_kernel does not fit on this device"; return fail(NPSWF_ERR_CUDA); }
         s.fit2_group16 = getenv("NPSWF_FIT2_GROUP") && atoi(getenv("NPSWF_FIT2_GROUP")) == 16;
         if (s.fit2_group16)
@@ -1050,6 +1074,43 @@ int npswf_debug_exp(npswf_handle *h, int64_t n, const double *x, double *y)
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaMemcpy(y, dy, (size_t)n * 8, cudaMemcpyDeviceToHost));
     cudaFree(dx); cudaFree(dy);
+    return 0;
+}
+
+// FP64 FMA-chain microbenchmark: 8 independent chains per thread, enough resident warps to saturate the pipe
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+        x0 = __fma_rn(x0, a, b); x1 = __fma_rn(x1, a, b); x2 = __fma_rn(x2, a, b); x3 = __fma_rn(x3, a, b);
+        x4 = __fma_rn(x4, a, b); x5 = __fma_rn(x5, a, b); x6 = __fma_rn(x6, a, b); x7 = __fma_rn(x7, a, b);
+    }
+    const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 123.456) out[0] = s;  // keeps the chains alive
+}
+
+int npswf_debug_fp64_peak(npswf_handle *h, double *gflops)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (!gflops) return NPSWF_ERR_ARG;
+    DevSlot &s = h->slots[0];
+    CU_TRY(h, cudaSetDevice(s.device));
+    double *d = nullptr;
+    CU_TRY(h, cudaMalloc(&d, 8));
+    cudaEvent_t e0, e1;
+    CU_TRY(h, cudaEventCreate(&e0));
+    CU_TRY(h, cudaEventCreate(&e1));
+    const int blocks = s.sm_count * 8, iters = 1 << 15;
+    fp64_peak_kernel<<<blocks, 256>>>(d, 1024, 0.999999, 1e-9);  // warm-up
+    CU_TRY(h, cudaEventRecord(e0));
+    fp64_peak_kernel<<<blocks, 256>>>(d, iters, 0.999999, 1e-9);
+    CU_TRY(h, cudaEventRecord(e1));
+    CU_TRY(h, cudaEventSynchronize(e1));
+    float ms = 0;
+    CU_TRY(h, cudaEventElapsedTime(&ms, e0, e1));
+    *gflops = 2.0 * 8.0 * (double)iters * 256.0 * blocks / (ms * 1e-3) / 1e9;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     return 0;
 }
 
