@@ -76,6 +76,7 @@ typedef struct NpsWfCounters {
     int64_t n_fit_attempted;   /* "fitted block-waveforms": present, passed threshold, npulse>0 */
     int64_t n_fit_ok_first, n_fit_ok_retry, n_fallback;
     int64_t n_pulses, n_peak_buffer_full, n_fit_iterations;
+    int64_t n_fit_evals;       /* chi2 + normal-equation passes over the 90 points (accepted + rejected + first) */
 } NpsWfCounters;
 
 typedef struct npswf_handle npswf_handle;

@@ -45,7 +45,7 @@ class NpsWfCalib(C.Structure):
 class NpsWfCounters(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "n_events", "n_block_waveforms", "n_present", "n_pass_threshold", "n_fit_attempted", "n_fit_ok_first",
-        "n_fit_ok_retry", "n_fallback", "n_pulses", "n_peak_buffer_full", "n_fit_iterations")]
+        "n_fit_ok_retry", "n_fallback", "n_pulses", "n_peak_buffer_full", "n_fit_iterations", "n_fit_evals")]
 
 
 EXPORTS = [

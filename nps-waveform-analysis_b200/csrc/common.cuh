@@ -108,7 +108,7 @@ constexpr int KN_LEN = 368;
 
 struct DeviceCounters {
     unsigned long long n_present, n_pass_threshold, n_fit_attempted, n_fit_ok_first, n_fit_ok_retry, n_fallback;
-    unsigned long long n_pulses, n_peak_buffer_full, n_fit_iterations;
+    unsigned long long n_pulses, n_peak_buffer_full, n_fit_iterations, n_fit_evals;
 };
 
 // Per-device read-only calibration (device pointers)

@@ -130,6 +130,17 @@ __device__ __forceinline__ bool solve_damped(const NormalEq<P> &ne, double lambd
     return pd;
 }
 
+// upper bound 2 g.dp of the chi2 decrease a Gauss-Newton step can achieve (the quadratic model gives
+// 2 g.dp - dp.H.dp and H is positive semi-definite)
+template <int P>
+__device__ __forceinline__ double lm_pred2(const NormalEq<P> &ne, const double (&dp)[P])
+{
+    double s = 0;
+#pragma unroll
+    for (int a = 0; a < P; a++) s = fma(ne.g[a], dp[a], s);
+    return 2.0 * s;
+}
+
 // cp.async (LDGSTS): global -> shared without staging registers; completion is awaited only at use time
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src)
 {
@@ -195,7 +206,7 @@ fit_small_kernel(const int *__restrict__ job_list, const int *__restrict__ job_c
     const int g = lane & (GROUP - 1);
     const int leader = lane & ~(GROUP - 1);
     const int njobs = *job_count;
-    unsigned long long c_ok1 = 0, c_ok2 = 0, c_fb = 0, c_it = 0, c_att = 0;
+    unsigned long long c_ok1 = 0, c_ok2 = 0, c_fb = 0, c_it = 0, c_att = 0, c_ev = 0;
 
     bool has_job = false, exhausted = false, fresh = false;
     long long item = 0;
@@ -300,10 +311,13 @@ fit_small_kernel(const int *__restrict__ job_list, const int *__restrict__ job_c
         const bool pd = fresh ? true : solve_damped<P>(cur, lambda, dp);
 #pragma unroll
         for (int i = 0; i < P; i++) trial[i] = par[i] + ((pd && !fresh) ? dp[i] : 0.0);
+        // predicted-decrease stop (see fit_thread_kernel): same rule, so a continued fit behaves as it would have there
+        const bool pre_done = has_job && !fresh && pd && lambda <= 1e-2 && lm_pred2<P>(cur, dp) < REL_TOL * (fabs(cur.c2) + 1e-30);
         NormalEq<P> nxt;
         eval_group<N, GROUP, true>(trial, y, w, g, spl4, nxt);
-        bool finished = false, converged = false;
-        if (has_job) {
+        bool finished = pre_done, converged = pre_done;
+        if (has_job && !pre_done) {
+            if (g == 0) c_ev++;
             if (fresh) {
                 cur = nxt;
                 fresh = false;
@@ -384,6 +398,7 @@ fit_small_kernel(const int *__restrict__ job_list, const int *__restrict__ job_c
         if (c_ok2) atomicAdd(&ctr->n_fit_ok_retry, c_ok2);
         if (c_fb) atomicAdd(&ctr->n_fallback, c_fb);
         if (c_it) atomicAdd(&ctr->n_fit_iterations, c_it);
+        if (c_ev) atomicAdd(&ctr->n_fit_evals, c_ev);
     }
 }
 

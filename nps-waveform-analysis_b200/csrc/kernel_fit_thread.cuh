@@ -26,11 +26,11 @@
 
 namespace npswf {
 
-constexpr int FT_WARPS = 3;
+constexpr int FT_WARPS = 4;   // 2 CTAs per SM = 2 warps per scheduler: what a 16 K-register sub-partition holds at 255 registers
 constexpr int FT_THREADS = FT_WARPS * 32;
 constexpr int FT_LD = 33;
 constexpr int FT_WARP_BYTES = NFIT * FT_LD * (int)sizeof(float2);   // (y, 1/err) per point
-constexpr size_t FT_SMEM = (size_t)FT_WARPS * FT_WARP_BYTES;         // 71 280 B -> 3 CTAs per SM
+constexpr size_t FT_SMEM = (size_t)FT_WARPS * FT_WARP_BYTES;         // 95 040 B -> 2 CTAs per SM
 constexpr int FT_CONT_STRIDE = 8;   // doubles per continuation record: par[P] | lambda | iters * 64 + rejects
 
 // 1 / Err (T2:946-956) as the binary32 weight the kernel stores: the same branch point as inv_err(), the
@@ -139,7 +139,7 @@ __device__ __forceinline__ void eval_thread(const double (&p)[2 * N + 1], const 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int N>
-__global__ void __launch_bounds__(FT_THREADS) __maxnreg__((N == 1) ? 224 : 255)
+__global__ void __launch_bounds__(FT_THREADS, 2)
 fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_count, int *__restrict__ job_next,
                   const double *__restrict__ signal, const double *__restrict__ corr_time_HMS, DevCalib cal, KParams kp,
                   double *__restrict__ wftime, double *__restrict__ wfampl, double *__restrict__ chi2_out,
@@ -157,7 +157,7 @@ fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
     const float2 *ywcol = ywwarp + lane;
     const int njobs = *job_count;
     const int max_tries = kp.fit_thread_tries;
-    unsigned long long c_ok1 = 0, c_it = 0, c_att = 0;
+    unsigned long long c_ok1 = 0, c_it = 0, c_att = 0, c_ev = 0;
 
     bool has_job = false, exhausted = false, fresh = false;
     long long item = 0;
@@ -273,11 +273,15 @@ fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
         const bool pd = fresh ? true : solve_damped<P>(cur, lambda, dp);
 #pragma unroll
         for (int i = 0; i < P; i++) trial[i] = par[i] + ((pd && !fresh) ? dp[i] : 0.0);
+        // predicted-decrease stop: in the Gauss-Newton regime chi2 cannot drop by more than 2 g.dp, so a step
+        // whose bound is below the tolerance is not worth its evaluation
+        const bool pre_done = has_job && !fresh && pd && lambda <= 1e-2 && lm_pred2<P>(cur, dp) < REL_TOL * (fabs(cur.c2) + 1e-30);
         NormalEq<P> nxt;
         eval_thread<N, U>(trial, ywcol, kn, nxt);
-        bool finished = false, handoff = false;
-        if (has_job) {
+        bool finished = pre_done, handoff = false;
+        if (has_job && !pre_done) {
             tries++;
+            c_ev++;
             if (fresh) {
                 cur = nxt;
                 fresh = false;
@@ -339,8 +343,10 @@ fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
             c_att += __shfl_xor_sync(FULL, c_att, o);
             c_ok1 += __shfl_xor_sync(FULL, c_ok1, o);
             c_it += __shfl_xor_sync(FULL, c_it, o);
+            c_ev += __shfl_xor_sync(FULL, c_ev, o);
         }
         if (lane == 0) {
+            if (c_ev) atomicAdd(&ctr->n_fit_evals, c_ev);
             if (c_att) atomicAdd(&ctr->n_fit_attempted, c_att);
             if (c_ok1) atomicAdd(&ctr->n_fit_ok_first, c_ok1);
             if (c_it) atomicAdd(&ctr->n_fit_iterations, c_it);

@@ -713,6 +713,10 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
             CR(cudaFuncSetAttribute(fit_thread_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(100, carve)));
             CR(cudaFuncSetAttribute(fit_thread_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(100, carve)));
         }
+        if (getenv("NPSWF_VERBOSE"))
+            fprintf(stderr, "npswf: resident CTAs per SM: front %d search %d fit_thread<1> %d fit_thread<2> %d fit_small %d/%d/%d fit<25> %d\n",
+                    s.occ_front, s.occ_search, s.occ_fit_thread[1], s.occ_fit_thread[2], s.occ_fit_small[1], s.occ_fit_small[2],
+                    s.occ_fit_small[3], s.occ_fit_big);
         if (s.occ_fit_thread[1] < 1 || s.occ_fit_thread[2] < 1) { h->err = "fit_thread_kernel does not fit on this device"; return fail(NPSWF_ERR_CUDA); }
         s.fit2_group16 = getenv("NPSWF_FIT2_GROUP") && atoi(getenv("NPSWF_FIT2_GROUP")) == 16;
         if (s.fit2_group16)
@@ -772,6 +776,7 @@ int npswf_get_counters(npswf_handle *h, NpsWfCounters *out)
         c.n_pulses += (int64_t)dc.n_pulses;
         c.n_peak_buffer_full += (int64_t)dc.n_peak_buffer_full;
         c.n_fit_iterations += (int64_t)dc.n_fit_iterations;
+        c.n_fit_evals += (int64_t)dc.n_fit_evals;
     }
     *out = c;
     return 0;

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(pkg):
 def test_struct_layout_matches_header(pkg):
     assert C.sizeof(pkg.NpsWfConfig) == 80
     assert C.sizeof(pkg.NpsWfCalib) == 40
-    assert C.sizeof(pkg.NpsWfCounters) == 88
+    assert C.sizeof(pkg.NpsWfCounters) == 96
 
 
 def test_derived_calibration_matches_oracle(pkg, calib, orc):

@@ -63,9 +63,10 @@ def main():
     h.sync_device(stream=st)
     wall = (time.perf_counter() - t0) / K * 1e3
     print("wall %.3f ms/step | " % wall, end="")
-    print("events %d steps %d cfg %d: per step front %.3f search %.3f fit %.3f ms | fits %d iters/fit %.2f retry %d fb %d" % (
+    print("events %d steps %d cfg %d: per step front %.3f search %.3f fit %.3f ms | fits %d iters/fit %.2f evals/fit %.2f retry %d fb %d" % (
         E, K, cfg, t["front_ms"] / K, t["search_ms"] / K, t["fit_ms"] / K, c["n_fit_attempted"] // K,
-        c["n_fit_iterations"] / max(1, c["n_fit_attempted"]), c["n_fit_ok_retry"], c["n_fallback"]))
+        c["n_fit_iterations"] / max(1, c["n_fit_attempted"]), c["n_fit_evals"] / max(1, c["n_fit_attempted"]),
+        c["n_fit_ok_retry"], c["n_fallback"]))
 
 
 if __name__ == "__main__":
