@@ -16,11 +16,18 @@ namespace npswf {
 constexpr int FS_THREADS = 128;
 constexpr int FS_MINB1 = 3, FS_MINB2 = 2, FS_MINB3 = 2;  // min resident CTAs per SM (register budget)
 
+// Normal equations of one fit.  H = J^T J is the Gauss-Newton matrix; s1 / s2 are the second-order terms of the
+// exact half-Hessian of chi2 that involve the pulse times (the model is linear in p0 and A):
+//   H_tt(n)  -=  sum r w A_n S''(x - t_n)   -> s2[n]        H_tA(n)  +=  sum r w S'(x - t_n)   -> s1[n]
+// (r = weighted residual).  They are always accumulated and only used once a fit has entered its slowly
+// converging phase (see solve_damped / the `newton` flag): with a large residual -- fewer pulses found than are
+// present -- Gauss-Newton converges linearly and needs 20-60 steps, the exact Hessian needs 2-4.
 template <int P>
 struct NormalEq {
     double H[P * (P + 1) / 2];  // lower triangle, row-packed
     double g[P];
     double c2;
+    double s1[(P - 1) / 2], s2[(P - 1) / 2];
 };
 
 template <int P, int GROUP>
@@ -33,6 +40,11 @@ __device__ __forceinline__ void group_reduce(NormalEq<P> &ne)
 #pragma unroll
         for (int i = 0; i < P; i++) ne.g[i] += __shfl_xor_sync(0xffffffffu, ne.g[i], o);
         ne.c2 += __shfl_xor_sync(0xffffffffu, ne.c2, o);
+#pragma unroll
+        for (int i = 0; i < (P - 1) / 2; i++) {
+            ne.s1[i] += __shfl_xor_sync(0xffffffffu, ne.s1[i], o);
+            ne.s2[i] += __shfl_xor_sync(0xffffffffu, ne.s2[i], o);
+        }
     }
 }
 
@@ -50,12 +62,15 @@ __device__ __forceinline__ void eval_group(const double (&par)[2 * N + 1], const
     for (int i = 0; i < P; i++) ne.g[i] = 0;
     ne.c2 = 0;
 #pragma unroll
+    for (int n = 0; n < N; n++) { ne.s1[n] = 0; ne.s2[n] = 0; }
+#pragma unroll
     for (int j = 0; j < PTS; j++) {
         const int k = g + GROUP * j;
         const double x = (double)(MFSTART + k);
         const double wk = w[j];  // 0 for the padding points k >= 90
         double val = par[0];
         double J[P];
+        double dsw[N], d2w[N];
         J[0] = wk;
 #pragma unroll
         for (int n = 0; n < N; n++) {
@@ -72,13 +87,22 @@ __device__ __forceinline__ void eval_group(const double (&par)[2 * N + 1], const
             if (WITH_J) {
                 double ds = q01.y + f * (2.0 * q23.x + 3.0 * f * q23.y);
                 ds = in ? ds : 0.0;
-                J[1 + 2 * n] = -par[2 + 2 * n] * ds * wk;
+                double d2 = 2.0 * q23.x + 6.0 * f * q23.y;
+                d2 = in ? d2 : 0.0;
+                dsw[n] = ds * wk;
+                d2w[n] = d2 * wk;
+                J[1 + 2 * n] = -par[2 + 2 * n] * dsw[n];
                 J[2 + 2 * n] = s * wk;
             }
         }
         const double r = (y[j] - val) * wk;
         ne.c2 += r * r;
         if (WITH_J) {
+#pragma unroll
+            for (int n = 0; n < N; n++) {
+                ne.s1[n] += r * dsw[n];
+                ne.s2[n] += r * d2w[n];
+            }
 #pragma unroll
             for (int a = 0; a < P; a++) {
                 ne.g[a] += J[a] * r;
@@ -87,22 +111,29 @@ __device__ __forceinline__ void eval_group(const double (&par)[2 * N + 1], const
             }
         }
     }
+#pragma unroll
+    for (int n = 0; n < N; n++) ne.s2[n] *= -par[2 + 2 * n];
     group_reduce<P, GROUP>(ne);
 }
 
-// (H + lambda diag(H)) dp = g by Cholesky, all in registers; one rsqrt per pivot, no divisions.
-// Returns false if the damped matrix is not positive definite.
+// (H + lambda |diag(H)|) dp = g by Cholesky, all in registers; one rsqrt per pivot, no divisions.
+// Returns false if the damped matrix is not positive definite.  With `newton` H is the exact half-Hessian
+// (Gauss-Newton matrix + the second-order terms s1, s2), which may be indefinite away from a minimum: the
+// caller then raises lambda exactly as for a rejected step.
 template <int P>
-__device__ __forceinline__ bool solve_damped(const NormalEq<P> &ne, double lambda, double (&dp)[P])
+__device__ __forceinline__ bool solve_damped(const NormalEq<P> &ne, double lambda, double (&dp)[P], bool newton = false)
 {
     double L[P * (P + 1) / 2];  // strict lower part; the diagonal slot holds 1 / L_aa
     bool pd = true;
+    const double nf = newton ? 1.0 : 0.0;
 #pragma unroll
     for (int a = 0; a < P; a++) {
 #pragma unroll
         for (int b = 0; b <= a; b++) {
             double s = ne.H[a * (a + 1) / 2 + b];
-            if (a == b) s += lambda * (s + 1e-12);
+            if (a == b && (a & 1)) s = fma(nf, ne.s2[(a - 1) / 2], s);                   // (t_n, t_n)
+            if (a == b + 1 && (b & 1)) s = fma(nf, ne.s1[(b - 1) / 2], s);               // (A_n, t_n)
+            if (a == b) s += lambda * (fabs(s) + 1e-12);
 #pragma unroll
             for (int k = 0; k < b; k++) s -= L[a * (a + 1) / 2 + k] * L[b * (b + 1) / 2 + k];
             if (a == b) {
@@ -216,6 +247,7 @@ fit_small_kernel(const int *__restrict__ job_list, const int *__restrict__ job_c
     NormalEq<P> cur;
     double lambda = 1e-3;
     int attempt = 1, max_iter = kp.fit_max_iter, iters = 0, it_total = 0, rejects = 0;
+    bool newton = false;   // exact-Hessian steps: switched on by the first accepted step that gains less than 5 %
 #pragma unroll
     for (int j = 0; j < PTS; j++) { y[j] = 0; w[j] = 0; }
 #pragma unroll
@@ -291,13 +323,14 @@ fit_small_kernel(const int *__restrict__ job_list, const int *__restrict__ job_c
                     __syncwarp(group_mask);  // the buffer may be refilled from here on
                     has_job = true; fresh = true;
                     lambda = 1e-3; attempt = 1; max_iter = kp.fit_max_iter; iters = 0; it_total = 0; rejects = 0;
+                    newton = false;
                     if (cont_state) {   // continuation of a fit started by fit_thread_kernel: its parameters, damping, counters
                         const double *cs = cont_state + (size_t)job_now * 8;
 #pragma unroll
                         for (int i = 0; i < P; i++) par[i] = cs[i];
                         lambda = cs[P];
                         const int pk = (int)cs[P + 1];
-                        iters = pk >> 6; rejects = pk & 63;
+                        iters = pk >> 7; rejects = (pk >> 1) & 63; newton = pk & 1;
                     }
                 } else {
                     exhausted = true;
@@ -308,7 +341,7 @@ fit_small_kernel(const int *__restrict__ job_list, const int *__restrict__ job_c
 
         // ---- one LM try (or the first evaluation of a fresh fit)
         double dp[P], trial[P];
-        const bool pd = fresh ? true : solve_damped<P>(cur, lambda, dp);
+        const bool pd = fresh ? true : solve_damped<P>(cur, lambda, dp, newton);
 #pragma unroll
         for (int i = 0; i < P; i++) trial[i] = par[i] + ((pd && !fresh) ? dp[i] : 0.0);
         // predicted-decrease stop (see fit_thread_kernel): same rule, so a continued fit behaves as it would have there
@@ -329,12 +362,13 @@ fit_small_kernel(const int *__restrict__ job_list, const int *__restrict__ job_c
                 lambda = fmax(lambda * 0.2, 1e-12);
                 rejects = 0;
                 iters++;
+                if (rel < 0.05) newton = true;
                 if (rel < REL_TOL) { converged = true; finished = true; }
                 else if (iters >= max_iter) {
                     if (attempt == 1) {  // retry from the same seeds, tougher configuration
 #pragma unroll
                         for (int i = 0; i < P; i++) par[i] = seed[i];
-                        fresh = true; lambda = 1.0; attempt = 2; max_iter = kp.fit_retry_max_iter;
+                        fresh = true; lambda = 1.0; attempt = 2; max_iter = kp.fit_retry_max_iter; newton = false;
                         it_total += iters; iters = 0; rejects = 0;
                     } else {
                         finished = true;

@@ -31,7 +31,7 @@ constexpr int FT_THREADS = FT_WARPS * 32;
 constexpr int FT_LD = 33;
 constexpr int FT_WARP_BYTES = NFIT * FT_LD * (int)sizeof(float2);   // (y, 1/err) per point
 constexpr size_t FT_SMEM = (size_t)FT_WARPS * FT_WARP_BYTES;         // 95 040 B -> 2 CTAs per SM
-constexpr int FT_CONT_STRIDE = 8;   // doubles per continuation record: par[P] | lambda | iters * 64 + rejects
+constexpr int FT_CONT_STRIDE = 8;   // doubles per continuation record: par[P] | lambda | iters << 7 | rejects << 1 | newton
 
 // 1 / Err (T2:946-956) as the binary32 weight the kernel stores: the same branch point as inv_err(), the
 // square root through the FP32 MUFU (relative error 2^-22, the storage format itself rounds at 2^-24; both
@@ -56,7 +56,7 @@ __device__ __forceinline__ void eval_thread(const double (&p)[2 * N + 1], const 
     static_assert(NFIT % (2 * U) == 0, "2 U must divide the number of fit points");
     const double2 *kp[N];
     double2 k0[N];
-    double wa[N], wb[N], wc[N], wd[N], dc[N], dd[N], nA[N];
+    double wa[N], wb[N], wc[N], wd[N], dc[N], dd[N], e0[N], e1[N], nA[N];
     int jlo[N];
     unsigned span[N];
 #pragma unroll
@@ -71,6 +71,7 @@ __device__ __forceinline__ void eval_thread(const double (&p)[2 * N + 1], const 
         wa[n] = g; wb[n] = f;
         wc[n] = (g * g * g - g) * (1.0 / 3.0); wd[n] = (f * f * f - f) * (1.0 / 3.0);
         dc[n] = (1.0 - 3.0 * g * g) * (1.0 / 3.0); dd[n] = (3.0 * f * f - 1.0) * (1.0 / 3.0);
+        e0[n] = 2.0 * g; e1[n] = 2.0 * f;   // S'' = 2 (g c0 + f c1)
         nA[n] = -p[2 + 2 * n];
         // 1 < u + j < 109  (T2:629)  <=>  jl <= j <= jh
         int jl = (int)floor(1.0 - u) + 1, jh = (int)ceil((double)(T - 1) - u) - 1;
@@ -86,6 +87,8 @@ __device__ __forceinline__ void eval_thread(const double (&p)[2 * N + 1], const 
 #pragma unroll
     for (int i = 0; i < P; i++) ne.g[i] = 0;
     ne.c2 = 0;
+#pragma unroll
+    for (int n = 0; n < N; n++) { ne.s1[n] = 0; ne.s2[n] = 0; }
     const double p0 = p[0];
     // two register buffers of U points each: while one is consumed the other is being loaded (no copies)
     float2 ywA[U], ywB[U];
@@ -105,6 +108,7 @@ __device__ __forceinline__ void eval_thread(const double (&p)[2 * N + 1], const 
             const double wk = (double)yw[u].y;
             double r = ((double)yw[u].x - p0) * wk;
             double J[P];
+            double dsw[N], d2w[N];
             J[0] = wk;
 #pragma unroll
             for (int n = 0; n < N; n++) {
@@ -112,12 +116,20 @@ __device__ __forceinline__ void eval_thread(const double (&p)[2 * N + 1], const 
                 const double wkm = ((unsigned)(j - jlo[n]) <= span[n]) ? wk : 0.0;   // in range: 1 < x - t < 109
                 const double s = fma(wd[n], k1.y, fma(wc[n], k0[n].y, fma(wb[n], k1.x, wa[n] * k0[n].x)));
                 const double ds = fma(dd[n], k1.y, fma(dc[n], k0[n].y, k1.x - k0[n].x));
+                const double d2 = fma(e1[n], k1.y, e0[n] * k0[n].y);
                 k0[n] = k1;
+                dsw[n] = ds * wkm;
+                d2w[n] = d2 * wkm;
                 J[2 + 2 * n] = s * wkm;
-                J[1 + 2 * n] = nA[n] * (ds * wkm);
+                J[1 + 2 * n] = nA[n] * dsw[n];
                 r = fma(nA[n], J[2 + 2 * n], r);
             }
             ne.c2 = fma(r, r, ne.c2);
+#pragma unroll
+            for (int n = 0; n < N; n++) {
+                ne.s1[n] = fma(r, dsw[n], ne.s1[n]);
+                ne.s2[n] = fma(r, d2w[n], ne.s2[n]);
+            }
 #pragma unroll
             for (int a = 0; a < P; a++) {
                 ne.g[a] = fma(J[a], r, ne.g[a]);
@@ -134,6 +146,8 @@ __device__ __forceinline__ void eval_thread(const double (&p)[2 * N + 1], const 
         if (j0 + 2 * U < NFIT) load(j0 + 2 * U, ywA, kA);
         consume(j0 + U, ywB, kB);
     }
+#pragma unroll
+    for (int n = 0; n < N; n++) ne.s2[n] *= nA[n];
 }
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -167,6 +181,7 @@ fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
     NormalEq<P> cur;
     double lambda = 1e-3;
     int iters = 0, rejects = 0, tries = 0;
+    bool newton = false;   // exact-Hessian steps (see NormalEq)
 #pragma unroll
     for (int i = 0; i < P; i++) par[i] = 0;
 #pragma unroll
@@ -263,14 +278,14 @@ fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
                 par[2 + 2 * n] = wfampl[(size_t)item * MAXP + n];               // wfampl             T2:663
             }
             has_job = true; fresh = true;
-            lambda = 1e-3; iters = 0; rejects = 0;
+            lambda = 1e-3; iters = 0; rejects = 0; newton = false;
             tries = inexact ? (1 << 20) : 0;   // samples not exact in binary32: hand the fit over after the seed evaluation
         }
         if (!__any_sync(FULL, has_job)) break;
 
         // ---- one LM try (or the first evaluation of a fresh fit)
         double dp[P], trial[P];
-        const bool pd = fresh ? true : solve_damped<P>(cur, lambda, dp);
+        const bool pd = fresh ? true : solve_damped<P>(cur, lambda, dp, newton);
 #pragma unroll
         for (int i = 0; i < P; i++) trial[i] = par[i] + ((pd && !fresh) ? dp[i] : 0.0);
         // predicted-decrease stop: in the Gauss-Newton regime chi2 cannot drop by more than 2 g.dp, so a step
@@ -293,6 +308,7 @@ fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
                 lambda = fmax(lambda * 0.2, 1e-12);
                 rejects = 0;
                 iters++;
+                if (rel < 0.05) newton = true;
                 if (rel < REL_TOL) finished = true;
                 else if (iters >= kp.fit_max_iter) handoff = true;   // the retry policy lives in fit_small_kernel
             } else {
@@ -309,7 +325,7 @@ fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
 #pragma unroll
             for (int i = 0; i < P; i++) cs[i] = par[i];
             cs[P] = lambda;
-            cs[P + 1] = (double)(iters * 64 + rejects);
+            cs[P + 1] = (double)((iters << 7) | (rejects << 1) | (newton ? 1 : 0));
             has_job = false;
         }
         // ---- write back converged fits (T2:796-827)
