@@ -325,7 +325,7 @@ fit_small_kernel(const int *__restrict__ job_list, const int *__restrict__ job_c
                     lambda = 1e-3; attempt = 1; max_iter = kp.fit_max_iter; iters = 0; it_total = 0; rejects = 0;
                     newton = false;
                     if (cont_state) {   // continuation of a fit started by fit_thread_kernel: its parameters, damping, counters
-                        const double *cs = cont_state + (size_t)job_now * 8;
+                        const double *cs = cont_state + (size_t)job_now * 10;
 #pragma unroll
                         for (int i = 0; i < P; i++) par[i] = cs[i];
                         lambda = cs[P];

@@ -31,7 +31,7 @@ constexpr int FT_THREADS = FT_WARPS * 32;
 constexpr int FT_LD = 33;
 constexpr int FT_WARP_BYTES = NFIT * FT_LD * (int)sizeof(float2);   // (y, 1/err) per point
 constexpr size_t FT_SMEM = (size_t)FT_WARPS * FT_WARP_BYTES;         // 95 040 B -> 2 CTAs per SM
-constexpr int FT_CONT_STRIDE = 8;   // doubles per continuation record: par[P] | lambda | iters << 7 | rejects << 1 | newton
+constexpr int FT_CONT_STRIDE = 10;  // doubles per continuation record: par[P] | lambda | iters << 7 | rejects << 1 | newton
 
 // 1 / Err (T2:946-956) as the binary32 weight the kernel stores: the same branch point as inv_err(), the
 // square root through the FP32 MUFU (relative error 2^-22, the storage format itself rounds at 2^-24; both
@@ -162,7 +162,7 @@ fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
                   double *__restrict__ cont_state)
 {
     constexpr int P = 2 * N + 1;
-    constexpr int U = (N == 1) ? 5 : 3;
+    constexpr int U = (N == 1) ? 5 : ((N == 2) ? 3 : 1);
     constexpr double REL_TOL = 1e-9;
     const unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char ft_smem[];

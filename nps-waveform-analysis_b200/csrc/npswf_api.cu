@@ -41,8 +41,8 @@ struct Workspace {  // per (device, pipeline stage) buffers for up to `cap` even
     uint8_t *status = nullptr;
     uint8_t *mask = nullptr;
     int *fit_count = nullptr;     // [64]: jobs per multiplicity, [16 + N]: job cursors, [32 + N]: continuation counts, [48 + N]: their cursors
-    int *cont_list = nullptr;     // [2][cap*B] fits handed from fit_thread_kernel to fit_small_kernel (N = 1, 2)
-    double *cont_state = nullptr; // [2][cap*B][8] their LM state
+    int *cont_list = nullptr;     // [3][cap*B] fits handed from fit_thread_kernel to fit_small_kernel (N = 1, 2, 3)
+    double *cont_state = nullptr; // [3][cap*B][10] their LM state
     int *bucket_count = nullptr;  // [13][B] jobs per (multiplicity, block)
     int *fit_list = nullptr;      // [13][B][cap] bucketed item ids
     int *fit_dense = nullptr;     // [13][cap*B] block-major dense job lists (what the fit kernels read)
@@ -65,7 +65,7 @@ struct DevSlot {
     bool fit_concurrent = true;  // env NPSWF_FIT_CONCURRENT=0 serialises the fit kernels on the caller's stream
     bool fit2_group16 = false;  // development knob (env NPSWF_FIT2_GROUP=16)
     bool fit_thread = true;     // thread-per-fit kernels for N = 1, 2 (env NPSWF_FIT_THREAD=0 selects the sub-warp kernels)
-    int occ_fit_thread[3] = {0, 3, 3};
+    int occ_fit_thread[4] = {0, 2, 2, 2};
     int fit_thread_maxocc = 0;  // env NPSWF_FIT_THREAD_OCC: cap on resident CTAs per SM (fewer CTAs leave more L1)
     int occ_front = 2, occ_search = 4, occ_fit_big = 1, occ_fit_small[4] = {0, 4, 4, 2};  // resident CTAs per SM
     std::vector<cudaEvent_t> prof_events;  // 4 per profiled chunk: start, after front, after search, after fits
@@ -178,8 +178,8 @@ int alloc_workspace(npswf_handle *h, DevSlot &s, Workspace &w, int64_t cap, bool
     if ((rc = dev_alloc(h, s, &w.minsig, nb))) return rc;
     if ((rc = dev_alloc(h, s, &w.flags, nb))) return rc;
     if ((rc = dev_alloc(h, s, &w.fit_count, 64))) return rc;
-    if ((rc = dev_alloc(h, s, &w.cont_list, (size_t)2 * nb))) return rc;
-    if ((rc = dev_alloc(h, s, &w.cont_state, (size_t)2 * nb * FT_CONT_STRIDE))) return rc;
+    if ((rc = dev_alloc(h, s, &w.cont_list, (size_t)3 * nb))) return rc;
+    if ((rc = dev_alloc(h, s, &w.cont_state, (size_t)3 * nb * FT_CONT_STRIDE))) return rc;
     if ((rc = dev_alloc(h, s, &w.bucket_count, (size_t)(MAXP + 1) * B))) return rc;
     if ((rc = dev_alloc(h, s, &w.fit_list, (size_t)(MAXP + 1) * nb))) return rc;
     if ((rc = dev_alloc(h, s, &w.fit_dense, (size_t)(MAXP + 1) * nb))) return rc;
@@ -313,36 +313,29 @@ int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, cons
         const int *list = w.fit_dense + (size_t)N * stride;
         const int *cnt = w.fit_count + N;
         int *next = w.fit_count + 16 + N;  // per-multiplicity job cursor, zeroed with fit_count
-        if (N <= 2 && s.fit_thread) {
-            // thread-per-fit for the first tries of every fit, then the sub-warp kernel on the fits handed over
+        if (N <= 3 && s.fit_thread) {
+            // thread-per-fit for the first tries of every fit, then the sub-warp kernel on the (rare) fits handed over
             int *ccnt = w.fit_count + 32 + N, *cnext = w.fit_count + 48 + N;
             int *clist = w.cont_list + (size_t)(N - 1) * stride;
             double *cstate = w.cont_state + (size_t)(N - 1) * stride * FT_CONT_STRIDE;
+            const int tgrid = s.sm_count * s.occ_fit_thread[N], sgrid = s.sm_count * 3;
             if (N == 1) {
-                fit_thread_kernel<1><<<s.sm_count * s.occ_fit_thread[1], FT_THREADS, FT_SMEM, st>>>(
+                fit_thread_kernel<1><<<tgrid, FT_THREADS, FT_SMEM, st>>>(
                     list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, ccnt, clist, cstate);
                 CU_TRY(h, cudaGetLastError());
-                if (s.cont_group == 32)
-                    fit_small_kernel<1, 32, 3><<<s.sm_count * 3, FS_THREADS, 0, st>>>(
-                        clist, ccnt, cnext, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, cstate);
-                else if (s.cont_group == 16)
-                    fit_small_kernel<1, 16, 3><<<s.sm_count * 3, FS_THREADS, 0, st>>>(
-                        clist, ccnt, cnext, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, cstate);
-                else
-                fit_small_kernel<1, 8, FS_MINB1><<<s.sm_count * s.occ_fit_small[1], FS_THREADS, 0, st>>>(
+                fit_small_kernel<1, 16, 3><<<sgrid, FS_THREADS, 0, st>>>(
+                    clist, ccnt, cnext, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, cstate);
+            } else if (N == 2) {
+                fit_thread_kernel<2><<<tgrid, FT_THREADS, FT_SMEM, st>>>(
+                    list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, ccnt, clist, cstate);
+                CU_TRY(h, cudaGetLastError());
+                fit_small_kernel<2, 16, 3><<<sgrid, FS_THREADS, 0, st>>>(
                     clist, ccnt, cnext, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, cstate);
             } else {
-                fit_thread_kernel<2><<<s.sm_count * s.occ_fit_thread[2], FT_THREADS, FT_SMEM, st>>>(
+                fit_thread_kernel<3><<<tgrid, FT_THREADS, FT_SMEM, st>>>(
                     list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, ccnt, clist, cstate);
                 CU_TRY(h, cudaGetLastError());
-                if (s.cont_group == 32)
-                    fit_small_kernel<2, 32, 3><<<s.sm_count * 3, FS_THREADS, 0, st>>>(
-                        clist, ccnt, cnext, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, cstate);
-                else if (s.cont_group == 16)
-                    fit_small_kernel<2, 16, 3><<<s.sm_count * 3, FS_THREADS, 0, st>>>(
-                        clist, ccnt, cnext, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, cstate);
-                else
-                fit_small_kernel<2, 8, FS_MINB2><<<s.sm_count * s.occ_fit_small[2], FS_THREADS, 0, st>>>(
+                fit_small_kernel<3, 16, FS_MINB3><<<s.sm_count * s.occ_fit_small[3], FS_THREADS, 0, st>>>(
                     clist, ccnt, cnext, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, cstate);
             }
         } else if (N == 1) {
@@ -704,11 +697,13 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
         s.fit_thread = !(getenv("NPSWF_FIT_THREAD") && atoi(getenv("NPSWF_FIT_THREAD")) == 0);
         CR(cudaFuncSetAttribute(fit_thread_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
         CR(cudaFuncSetAttribute(fit_thread_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
+        CR(cudaFuncSetAttribute(fit_thread_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
+        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_thread[3], fit_thread_kernel<3>, FT_THREADS, FT_SMEM));
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_thread[1], fit_thread_kernel<1>, FT_THREADS, FT_SMEM));
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_thread[2], fit_thread_kernel<2>, FT_THREADS, FT_SMEM));
         if (getenv("NPSWF_FIT_THREAD_OCC")) s.fit_thread_maxocc = atoi(getenv("NPSWF_FIT_THREAD_OCC"));
         if (s.fit_thread_maxocc > 0) {
-            for (int n = 1; n <= 2; n++) s.occ_fit_thread[n] = std::min(s.occ_fit_thread[n], s.fit_thread_maxocc);
+            for (int n = 1; n <= 3; n++) s.occ_fit_thread[n] = std::min(s.occ_fit_thread[n], s.fit_thread_maxocc);
             const int carve = (int)((s.fit_thread_maxocc * (FT_SMEM + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
             CR(cudaFuncSetAttribute(fit_thread_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(100, carve)));
             CR(cudaFuncSetAttribute(fit_thread_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(100, carve)));
@@ -717,7 +712,7 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
             fprintf(stderr, "npswf: resident CTAs per SM: front %d search %d fit_thread<1> %d fit_thread<2> %d fit_small %d/%d/%d fit<25> %d\n",
                     s.occ_front, s.occ_search, s.occ_fit_thread[1], s.occ_fit_thread[2], s.occ_fit_small[1], s.occ_fit_small[2],
                     s.occ_fit_small[3], s.occ_fit_big);
-        if (s.occ_fit_thread[1] < 1 || s.occ_fit_thread[2] < 1) { h->err = "fit_thread_kernel does not fit on this device"; return fail(NPSWF_ERR_CUDA); }
+        if (s.occ_fit_thread[1] < 1 || s.occ_fit_thread[2] < 1 || s.occ_fit_thread[3] < 1) { h->err = "fit_thread_kernel does not fit on this device"; return fail(NPSWF_ERR_CUDA); }
         s.fit2_group16 = getenv("NPSWF_FIT2_GROUP") && atoi(getenv("NPSWF_FIT2_GROUP")) == 16;
         if (s.fit2_group16)
             CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_small[2], fit_small_kernel<2, 16, 3>, FS_THREADS, 0));
