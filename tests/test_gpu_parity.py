@@ -257,3 +257,82 @@ def test_device_entry_point_equals_host_entry_point(gpu, events):
     torch.cuda.synchronize()
     for k in host:
         assert np.array_equal(o[k].cpu().numpy(), host[k]), k
+
+
+def _device_analyze(h, ev, E):
+    import torch
+    dev = torch.device("cuda:0")
+    sig = torch.from_numpy(ev["signal"][:E]).to(dev); pres = torch.from_numpy(ev["pres"][:E]).to(dev)
+    corr = torch.from_numpy(ev["corr_time_HMS"][:E]).to(dev)
+    o = dict(wfnpulse=torch.empty((E, 1080), dtype=torch.int32, device=dev),
+             wftime=torch.empty((E, 1080, 12), dtype=torch.float64, device=dev),
+             wfampl=torch.empty((E, 1080, 12), dtype=torch.float64, device=dev),
+             chi2=torch.empty((E, 1080), dtype=torch.float64, device=dev),
+             timewf=torch.empty((E, 1080), dtype=torch.float64, device=dev),
+             amplwf=torch.empty((E, 1080), dtype=torch.float64, device=dev),
+             status=torch.empty((E, 1080), dtype=torch.uint8, device=dev))
+    stream = torch.cuda.Stream()
+    h.analyze_device(E, sig.data_ptr(), pres.data_ptr(), corr.data_ptr(), o["wfnpulse"].data_ptr(),
+                     o["wftime"].data_ptr(), o["wfampl"].data_ptr(), o["chi2"].data_ptr(), o["timewf"].data_ptr(),
+                     o["amplwf"].data_ptr(), o["status"].data_ptr(), stream=stream.cuda_stream)
+    h.sync_device(stream=stream.cuda_stream)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in o.items()}
+
+
+def test_overlapped_chunks_equal_serialised(pkg, calib, spline):
+    """Device path with several chunks: chunks on alternating internal streams + fit kernels on side streams
+    (profiling off) give bit-identical outputs to the fully serialised order (profiling on)."""
+    E = 500
+    ev = synth.generate_host(synth.config_params(2, absent_frac=0.02), spline, calib, 70000, E, n_threads=8)
+    h = pkg.NpsWf(calib, chunk_events=148)
+    h.set_profiling(False)
+    a = _device_analyze(h, ev, E)
+    h.set_profiling(True)
+    b = _device_analyze(h, ev, E)
+    t = h.stage_times(reset=True)
+    assert t["chunks"] == 4 and t["front_ms"] > 0 and t["search_ms"] > 0 and t["fit_ms"] > 0
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    assert ((a["status"] & 28) > 0).sum() > 0.8 * E * 1080
+
+
+def test_thread_fit_handoff_reaches_the_same_minimum(pkg, calib, events, monkeypatch):
+    """A fit that the thread-per-fit kernel hands to the sub-warp kernel after 2 tries ends where the same fit
+    ends when the thread kernel is allowed to finish it: same status, same minimum to ~1e-6 bin."""
+    ev = events[2]
+    base = pkg.NpsWf(calib).analyze(ev["signal"], ev["pres"], ev["corr_time_HMS"])
+    monkeypatch.setenv("NPSWF_FIT_THREAD_TRIES", "2")
+    h2 = pkg.NpsWf(calib)
+    monkeypatch.delenv("NPSWF_FIT_THREAD_TRIES")
+    got = h2.analyze(ev["signal"], ev["pres"], ev["corr_time_HMS"])
+    assert np.array_equal(got["wfnpulse"], base["wfnpulse"])
+    fit = ((base["status"] & 12) > 0) & (base["wfnpulse"] <= 3)
+    assert np.array_equal(got["status"][fit], base["status"][fit])
+    valid = (np.arange(12)[None, None, :] < base["wfnpulse"][..., None]) & fit[..., None]
+    assert np.abs(got["wftime"][valid] - base["wftime"][valid]).max() < 4e-5          # ns (1e-5 bin)
+    # (the thread kernel keeps the weights 1/Err in binary32, the sub-warp kernel in binary64: chi2 differs at 1e-7)
+    assert (np.abs(got["chi2"][fit] - base["chi2"][fit]) <= 2e-6 * np.abs(base["chi2"][fit])).all()
+
+
+def test_off_lattice_traces_are_fitted_unrounded(gpu, events):
+    """Samples that are not exact in binary32 must not be rounded: such a trace takes the generic double
+    path.  A 1e-13 mV perturbation (far below binary32 resolution) must move the fit by ~1e-13, not by ~1e-8."""
+    ev = events[1]
+    sig = ev["signal"].copy()
+    base = gpu.analyze(sig, ev["pres"], ev["corr_time_HMS"])
+    rng = np.random.default_rng(3)
+    sig2 = sig + rng.uniform(0.5e-13, 1e-13, sig.shape)
+    assert not np.array_equal(sig2.astype(np.float32).astype(np.float64), sig2)
+    got = gpu.analyze(sig2, ev["pres"], ev["corr_time_HMS"])
+    assert np.array_equal(got["wfnpulse"], base["wfnpulse"])
+    fit = ((base["status"] & 12) > 0) & ((got["status"] & 12) > 0)
+    assert fit.sum() > 3000
+    valid = (np.arange(12)[None, None, :] < base["wfnpulse"][..., None]) & fit[..., None]
+    assert np.abs(got["wftime"][valid] - base["wftime"][valid]).max() < 1e-6
+    assert np.abs(got["wfampl"][valid] - base["wfampl"][valid]).max() < 1e-6
+
+
+def test_fp64_peak_tap(gpu):
+    g = gpu.fp64_peak_gflops()
+    assert 5e3 < g < 1e5, g   # B200: ~3.4e4 GFLOP/s measured
