@@ -47,6 +47,7 @@ struct Workspace {  // per (device, pipeline stage) buffers for up to `cap` even
     int *fit_list = nullptr;      // [13][B][cap] bucketed item ids
     int *fit_dense = nullptr;     // [13][cap*B] block-major dense job lists (what the fit kernels read)
     cudaStream_t stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_cmp = nullptr, ev_out = nullptr;  // host-path pipeline: uploaded / computed / downloaded
     bool io = false;  // has the signal/pres/output staging buffers (host-buffer API) or only scratch
 };
 
@@ -58,7 +59,7 @@ struct DevSlot {
     Workspace ws[2];
     DeviceCounters *ctr = nullptr;
     const double *gold1 = nullptr;  // [2][138] first-iteration Gold denominators and reciprocals
-    cudaStream_t own_stream = nullptr;
+    cudaStream_t own_stream = nullptr, copy_in = nullptr, copy_out = nullptr;
     cudaStream_t fit_stream[4] = {nullptr, nullptr, nullptr, nullptr};  // N = 1 | N = 2 | N = 3 | N >= 4 run concurrently
     cudaEvent_t fit_fork = nullptr, fit_join[4] = {nullptr, nullptr, nullptr, nullptr}, chunk_join[2] = {nullptr, nullptr};
     int cont_group = 16;  // lanes per fit of the continuation kernels (env NPSWF_CONT_GROUP)
@@ -184,6 +185,9 @@ int alloc_workspace(npswf_handle *h, DevSlot &s, Workspace &w, int64_t cap, bool
     if ((rc = dev_alloc(h, s, &w.fit_list, (size_t)(MAXP + 1) * nb))) return rc;
     if ((rc = dev_alloc(h, s, &w.fit_dense, (size_t)(MAXP + 1) * nb))) return rc;
     CU_TRY(h, cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+    CU_TRY(h, cudaEventCreateWithFlags(&w.ev_in, cudaEventDisableTiming));
+    CU_TRY(h, cudaEventCreateWithFlags(&w.ev_cmp, cudaEventDisableTiming));
+    CU_TRY(h, cudaEventCreateWithFlags(&w.ev_out, cudaEventDisableTiming));
     return 0;
 }
 
@@ -451,39 +455,59 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
     CU_TRY(h, cudaSetDevice(s.device));
     int rc = ensure_io(h, s);
     if (rc) return rc;
+    // Host buffers: a three-stage pipeline over the two workspaces -- uploads on their own stream, every kernel on
+    // one compute stream (two chunks computing side by side would only fight for shared memory), downloads on a
+    // third stream -- so the copy engines of both directions run under the kernels of the neighbouring chunks.
+    // About eight chunks per call (multiples of 148 events, at least 296) keep the uncovered first upload and
+    // last download short.
+    int64_t chunk = h->chunk;
+    if (hi - lo > 2 * 296) chunk = std::min<int64_t>(h->chunk, std::max<int64_t>(296, ((hi - lo + 8 * 148 - 1) / (8 * 148)) * 148));
+    cudaStream_t s_in = s.copy_in, s_out = s.copy_out, s_cmp = s.ws[0].stream;
     int which = 0;
-    for (int64_t e0 = lo; e0 < hi; e0 += h->chunk, which ^= 1) {
+    int64_t k = 0;
+    for (int64_t e0 = lo; e0 < hi; e0 += chunk, which ^= 1, k++) {
         Workspace &w = s.ws[which];
-        cudaStream_t st = w.stream;
-        const int64_t n = std::min<int64_t>(h->chunk, hi - e0);
+        const int64_t n = std::min<int64_t>(chunk, hi - e0);
         const size_t nb = (size_t)n * B, ob = (size_t)e0 * B;
+        // upload: the workspace must have been drained by the download of chunk k - 2
+        if (k >= 2) CU_TRY(h, cudaStreamWaitEvent(s_in, w.ev_out, 0));
         if (io.counts) {
             if (!w.counts) {
                 if ((rc = dev_alloc(h, s, &w.counts, (size_t)w.cap * B * T))) return rc;
             }
-            CU_TRY(h, cudaMemcpyAsync(w.counts, io.counts + ob * T, nb * T * sizeof(int16_t), cudaMemcpyHostToDevice, st));
-            const long long tot = (long long)nb * T;
-            widen_counts_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(w.counts, w.signal, io.lsb, tot);
-            CU_TRY(h, cudaGetLastError());
+            CU_TRY(h, cudaMemcpyAsync(w.counts, io.counts + ob * T, nb * T * sizeof(int16_t), cudaMemcpyHostToDevice, s_in));
         } else {
-            CU_TRY(h, cudaMemcpyAsync(w.signal, io.signal + ob * T, nb * T * sizeof(double), cudaMemcpyHostToDevice, st));
+            CU_TRY(h, cudaMemcpyAsync(w.signal, io.signal + ob * T, nb * T * sizeof(double), cudaMemcpyHostToDevice, s_in));
         }
-        CU_TRY(h, cudaMemcpyAsync(w.pres, io.pres + ob, nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        if (io.corr) CU_TRY(h, cudaMemcpyAsync(w.corr, io.corr + e0, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
-        else CU_TRY(h, cudaMemsetAsync(w.corr, 0, (size_t)n * sizeof(double), st));
-        rc = run_chunk(h, s, w, st, n, w.signal, w.pres, w.corr, w.wfnpulse, w.wftime, w.wfampl, w.chi2, w.timewf,
+        CU_TRY(h, cudaMemcpyAsync(w.pres, io.pres + ob, nb * sizeof(int32_t), cudaMemcpyHostToDevice, s_in));
+        if (io.corr) CU_TRY(h, cudaMemcpyAsync(w.corr, io.corr + e0, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s_in));
+        else CU_TRY(h, cudaMemsetAsync(w.corr, 0, (size_t)n * sizeof(double), s_in));
+        CU_TRY(h, cudaEventRecord(w.ev_in, s_in));
+        // compute
+        CU_TRY(h, cudaStreamWaitEvent(s_cmp, w.ev_in, 0));
+        if (io.counts) {
+            const long long tot = (long long)nb * T;
+            widen_counts_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s_cmp>>>(w.counts, w.signal, io.lsb, tot);
+            CU_TRY(h, cudaGetLastError());
+        }
+        rc = run_chunk(h, s, w, s_cmp, n, w.signal, w.pres, w.corr, w.wfnpulse, w.wftime, w.wfampl, w.chi2, w.timewf,
                        w.amplwf, w.status);
         if (rc) return rc;
-        if (io.wfnpulse) CU_TRY(h, cudaMemcpyAsync(io.wfnpulse + ob, w.wfnpulse, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        if (io.wftime) CU_TRY(h, cudaMemcpyAsync(io.wftime + ob * MAXP, w.wftime, nb * MAXP * sizeof(double), cudaMemcpyDeviceToHost, st));
-        if (io.wfampl) CU_TRY(h, cudaMemcpyAsync(io.wfampl + ob * MAXP, w.wfampl, nb * MAXP * sizeof(double), cudaMemcpyDeviceToHost, st));
-        if (io.chi2) CU_TRY(h, cudaMemcpyAsync(io.chi2 + ob, w.chi2, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
-        if (io.timewf) CU_TRY(h, cudaMemcpyAsync(io.timewf + ob, w.timewf, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
-        if (io.amplwf) CU_TRY(h, cudaMemcpyAsync(io.amplwf + ob, w.amplwf, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
-        if (io.status) CU_TRY(h, cudaMemcpyAsync(io.status + ob, w.status, nb * sizeof(uint8_t), cudaMemcpyDeviceToHost, st));
+        CU_TRY(h, cudaEventRecord(w.ev_cmp, s_cmp));
+        // download
+        CU_TRY(h, cudaStreamWaitEvent(s_out, w.ev_cmp, 0));
+        if (io.wfnpulse) CU_TRY(h, cudaMemcpyAsync(io.wfnpulse + ob, w.wfnpulse, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s_out));
+        if (io.wftime) CU_TRY(h, cudaMemcpyAsync(io.wftime + ob * MAXP, w.wftime, nb * MAXP * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+        if (io.wfampl) CU_TRY(h, cudaMemcpyAsync(io.wfampl + ob * MAXP, w.wfampl, nb * MAXP * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+        if (io.chi2) CU_TRY(h, cudaMemcpyAsync(io.chi2 + ob, w.chi2, nb * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+        if (io.timewf) CU_TRY(h, cudaMemcpyAsync(io.timewf + ob, w.timewf, nb * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+        if (io.amplwf) CU_TRY(h, cudaMemcpyAsync(io.amplwf + ob, w.amplwf, nb * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+        if (io.status) CU_TRY(h, cudaMemcpyAsync(io.status + ob, w.status, nb * sizeof(uint8_t), cudaMemcpyDeviceToHost, s_out));
+        CU_TRY(h, cudaEventRecord(w.ev_out, s_out));
     }
-    CU_TRY(h, cudaStreamSynchronize(s.ws[0].stream));
-    CU_TRY(h, cudaStreamSynchronize(s.ws[1].stream));
+    CU_TRY(h, cudaStreamSynchronize(s_in));
+    CU_TRY(h, cudaStreamSynchronize(s_cmp));
+    CU_TRY(h, cudaStreamSynchronize(s_out));
     return fold_profile(h, s);
 }
 
@@ -675,6 +699,8 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
         if ((rc = dev_alloc(h, s, &s.ctr, 1))) return fail(rc);
         CR(cudaMemset(s.ctr, 0, sizeof(DeviceCounters)));
         CR(cudaStreamCreateWithFlags(&s.own_stream, cudaStreamNonBlocking));
+        CR(cudaStreamCreateWithFlags(&s.copy_in, cudaStreamNonBlocking));
+        CR(cudaStreamCreateWithFlags(&s.copy_out, cudaStreamNonBlocking));
         if (getenv("NPSWF_CONT_GROUP")) s.cont_group = atoi(getenv("NPSWF_CONT_GROUP"));
         s.fit_concurrent = !(getenv("NPSWF_FIT_CONCURRENT") && atoi(getenv("NPSWF_FIT_CONCURRENT")) == 0);
         CR(cudaEventCreateWithFlags(&s.fit_fork, cudaEventDisableTiming));
@@ -739,6 +765,13 @@ void npswf_destroy(npswf_handle *h)
         for (int i = 0; i < 2; i++)
             if (s.ws[i].stream) cudaStreamDestroy(s.ws[i].stream);
         if (s.own_stream) cudaStreamDestroy(s.own_stream);
+        if (s.copy_in) cudaStreamDestroy(s.copy_in);
+        if (s.copy_out) cudaStreamDestroy(s.copy_out);
+        for (int i = 0; i < 2; i++) {
+            if (s.ws[i].ev_in) cudaEventDestroy(s.ws[i].ev_in);
+            if (s.ws[i].ev_cmp) cudaEventDestroy(s.ws[i].ev_cmp);
+            if (s.ws[i].ev_out) cudaEventDestroy(s.ws[i].ev_out);
+        }
         for (int i = 0; i < 4; i++) {
             if (s.fit_stream[i]) cudaStreamDestroy(s.fit_stream[i]);
             if (s.fit_join[i]) cudaEventDestroy(s.fit_join[i]);
