@@ -116,6 +116,8 @@ struct DevCalib {
     const double *mfyref;    // [B][11]
     const double *mfint;     // [B]
     const double *mfrecip;   // [B] RN(1/mfint)
+    const double *mfc;       // [B][11] RN(mfyref * RN(1/mfint)): taps of the fast matched-filter evaluation
+    const double *mfepsf;    // [B] 2^-47 * sum|mfyref| * |1/mfint| (1 + 1e-9): error-bound factor of that evaluation
     const double *timeref;   // [B]
     const float *cortime;    // [B]
     const int32_t *preswf;   // [B]

@@ -581,7 +581,7 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
     h->mfint.assign(B, 0.0);
     h->spline.assign((size_t)B * (T - 1) * 4, 0.0);
     h->timeref.assign(cal->timeref, cal->timeref + B);
-    std::vector<double> mfrecip(B, 0.0);
+    std::vector<double> mfrecip(B, 0.0), mfc((size_t)B * MFW, 0.0), mfepsf(B, 0.0);
     for (int i = 0; i < B; i++) {
         if (cal->preswf[i] != 1) continue;
         const double *X = cal->interpX + (size_t)i * T, *Y = cal->interpY + (size_t)i * T;
@@ -618,6 +618,14 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
             return NPSWF_ERR_CALIB;
         }
         mfrecip[i] = 1.0 / h->mfint[i];
+        {
+            double sabs = 0.0;
+            for (int jt = 0; jt < MFW; jt++) {
+                mfc[(size_t)i * MFW + jt] = h->mfyref[(size_t)i * MFW + jt] * mfrecip[i];
+                sabs += std::fabs(h->mfyref[(size_t)i * MFW + jt]);
+            }
+            mfepsf[i] = std::ldexp(sabs * std::fabs(mfrecip[i]) * (1.0 + 1e-9), -47);
+        }
         build_spline(X, Y, &h->spline[(size_t)i * (T - 1) * 4]);
     }
     // ---- devices
@@ -672,6 +680,8 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
         if ((rc = dev_upload(h, s, &s.cal.mfyref, h->mfyref.data(), h->mfyref.size()))) return fail(rc);
         if ((rc = dev_upload(h, s, &s.cal.mfint, h->mfint.data(), h->mfint.size()))) return fail(rc);
         if ((rc = dev_upload(h, s, &s.cal.mfrecip, mfrecip.data(), mfrecip.size()))) return fail(rc);
+        if ((rc = dev_upload(h, s, &s.cal.mfc, mfc.data(), mfc.size()))) return fail(rc);
+        if ((rc = dev_upload(h, s, &s.cal.mfepsf, mfepsf.data(), mfepsf.size()))) return fail(rc);
         if ((rc = dev_upload(h, s, &s.cal.timeref, cal->timeref, (size_t)B))) return fail(rc);
         if ((rc = dev_upload(h, s, &s.cal.cortime, cal->cortime, (size_t)B))) return fail(rc);
         if ((rc = dev_upload(h, s, &s.cal.preswf, cal->preswf, (size_t)B))) return fail(rc);

@@ -50,6 +50,44 @@ def test_matched_filter_bit_exact(gpu, orc, events, cfg):
                 assert np.array_equal(mf[e, b], orc.matched_filter(b, ev["signal"][e])[1]), (cfg, e, b)
 
 
+def test_matched_filter_bit_exact_adversarial(gpu, orc):
+    """The matched filter is evaluated fast + error bound + exact re-evaluation of undecided outputs: arbitrary
+    (off-lattice) doubles over 9 orders of magnitude, flat traces (every output ties for the minimum), repeated
+    minima, a huge pulse on a quiet baseline, negative pedestals -- every stored float must equal the oracle's."""
+    rng = np.random.default_rng(17)
+    sig = np.zeros((4, 1080, 110))
+    x = np.arange(110.0)
+    for b in range(1080):
+        kind = b % 9
+        if kind == 0:
+            sig[:, b] = rng.normal(0.0, 0.3, (4, 110)) * 10.0 ** rng.uniform(-4, 5)
+        elif kind == 1:
+            sig[:, b] = rng.uniform(-50, 50)                                   # flat
+        elif kind == 2:
+            sig[:, b] = np.round(rng.normal(0, 1.0, (4, 110)) * 4) / 4        # coarse lattice: many exact ties
+        elif kind == 3:
+            sig[:, b] = rng.normal(0, 0.3, (4, 110)) + 1.0e4 * np.exp(-0.5 * ((x - rng.uniform(20, 90)) / 2.5) ** 2)
+        elif kind == 4:
+            sig[:, b] = -200.0 + rng.normal(0, 0.01, (4, 110))
+        elif kind == 5:
+            sig[:, b] = np.tile(rng.normal(0, 1, 11), 10)                      # periodic with the filter length
+        elif kind == 6:
+            sig[:, b] = rng.normal(0, 0.3, (4, 110)) + rng.uniform(3, 500) * np.exp(-0.5 * ((x - rng.uniform(15, 95)) / 3.0) ** 2)
+        elif kind == 7:
+            sig[:, b] = rng.standard_cauchy((4, 110))
+        else:
+            sig[:, b] = (rng.integers(0, 4096, (4, 110)) - 300) * synth.LSB
+    pres = np.ones((4, 1080), np.int32)
+    mf = gpu.matched_filter(sig, pres)
+    bad = 0
+    for e in range(4):
+        for b in range(1080):
+            ref = orc.matched_filter(b, sig[e])[1]
+            if not np.array_equal(mf[e, b], ref):
+                bad += 1
+                assert bad < 0, (e, b, b % 9, np.nonzero(mf[e, b] != ref)[0][:8], mf[e, b][mf[e, b] != ref][:4], ref[mf[e, b] != ref][:4])
+
+
 def test_tspectrum_intermediates_bit_exact(gpu, orc, events):
     """Markov smoothing, Gold deconvolution and fPositionX against the oracle, bitwise."""
     hists = []
