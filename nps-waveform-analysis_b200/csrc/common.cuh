@@ -121,6 +121,8 @@ struct DevCalib {
     const double *timeref;   // [B]
     const float *cortime;    // [B]
     const int32_t *preswf;   // [B]
+    const int32_t *win_lo;   // [B] first time bin with |it - (timeref + timerefacc)| < coinc_width (T2:267); 1 << 20 if none
+    const int32_t *win_span; // [B] last - first bin of that window
     const double *spline;    // [B][109][4] = y, b, c, d
     const double2 *knots;    // [B][KN_LEN] = (y_i, c_i = y''_i / 2) at knot i - KN_LO, zero outside 0..109
 };

@@ -19,7 +19,7 @@ namespace npswf {
 constexpr int FRONT_THREADS = 256;
 constexpr int FRONT_WARPS = FRONT_THREADS / 32;
 constexpr int FRONT_RING = 4;
-constexpr size_t FRONT_SMEM = (size_t)FRONT_RING * ROW_BYTES + 64 /*mbarriers*/ + 1088 /*pres bytes*/ + 16;
+constexpr size_t FRONT_SMEM = (size_t)FRONT_RING * ROW_BYTES + 64 /*mbarriers*/ + 1088 /*pres bytes*/ + 16 + 1024 /*zero trace*/;
 
 // flags byte written per (event, block)
 constexpr uint8_t FL_PRESENT = 1, FL_OKTOFIT = 2;
@@ -39,6 +39,10 @@ __device__ __noinline__ double mf_exact_output(const double *s /* the block's 11
     return a;
 }
 
+// min / max of doubles as one compare + select (no NaN canonicalisation: the inputs are finite)
+__device__ __forceinline__ double dmin2(double a, double b) { return b < a ? b : a; }
+__device__ __forceinline__ double dmax2(double a, double b) { return b > a ? b : a; }
+
 // Half-warp task: matched filter of one block.  hl = lane & 15 owns outputs it = 5 + 7*hl + o.
 //
 // What is stored is float(acc[it] - min acc) (T2:170, TH1F storage T2:178), and the float rounding hides almost
@@ -48,101 +52,109 @@ __device__ __noinline__ double mf_exact_output(const double *s /* the block's 11
 //     (standard rounding-error bounds: 12.1 u S for the reference's order, 13.1 u S for the chain, S = sum |terms|);
 //   * every output within 2.5 eps of the smallest F could be the reference's minimum: those (normally one) are
 //     recomputed exactly and give the exact minimum Emin;
-//   * for every other output w = F - Emin is within eta = 2 eps + 2^-49 |w| of the reference's E - Emin; if
+//   * for every other output w = F - Emin is within eta = 2 eps + 2^-49 |w| <= 2.5 eps of the reference's E - Emin; if
 //     float(w - eta) == float(w + eta) the stored float is decided, otherwise (probability ~1e-4 per output) the
 //     output is recomputed exactly.
 // The result is bit-identical to the exact evaluation by construction, at ~1/4 of its FP64 work.
+// `s` may be read up to 12 samples past the end of the trace (the next trace of the ring, or the barrier area):
+// such values only reach outputs that are not stored.
 __device__ __forceinline__ void mf_block_halfwarp(const double *__restrict__ s, int lane_in_warp, bool active,
                                                   const double *__restrict__ kern /*mfyref[b][0..10]*/,
                                                   const double *__restrict__ kc /*mfc[b][0..10]*/, double mfint,
                                                   double mfrecip, double epsf, float *__restrict__ mf_out,
                                                   double *minsig_out)
 {
-    // the 17 samples this lane's 7 outputs need: indices 7*hl .. 7*hl+16
+    const unsigned FULL = 0xffffffffu;
     const int hl = lane_in_warp & 15;
-    double v[17];
+    const int half = lane_in_warp & 16;
     const int base = 7 * hl;
+    // the 17 samples this lane's 7 outputs need: indices 7*hl .. 7*hl+16
+    double v[17];
 #pragma unroll
-    for (int j = 0; j < 17; j++) v[j] = (active && base + j < T) ? s[base + j] : 0.0;
-    // minsignal: init 1e6 (T2:550), min over the trace (T2:884); each lane covers its first 7 samples
-    double mn = 1.0e6, mx = -1.0e300;
+    for (int j = 0; j < 17; j++) v[j] = s[base + j];
+    // minsignal: init 1e6 (T2:550), min over the trace (T2:884); each lane covers its first 7 samples, lane 15 the
+    // last 5 (indices 110, 111 do not exist: it re-reads 109)
+    double mn = 1.0e6;
+    double own[7];
 #pragma unroll
-    for (int j = 0; j < 7; j++)
-        if (base + j < T) { mn = fmin(mn, v[j]); mx = fmax(mx, v[j]); }
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    for (int j = 0; j < 7; j++) {
+        own[j] = (j < 5) ? v[j] : s[min(base + j, T - 1)];
+        mn = dmin2(mn, own[j]);
     }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) mn = dmin2(mn, __shfl_xor_sync(FULL, mn, o));
+    // an upper bound of max(trace) - min(trace) for the error bound: the differences are >= 0, so their order is the
+    // order of their high words as integers; the bound is the largest high word + 1 with a zero low word
+    int dhi = 0;
+#pragma unroll
+    for (int j = 0; j < 7; j++) dhi = max(dhi, __double2hiint(dsub(own[j], mn)));
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) dhi = max(dhi, __shfl_xor_sync(FULL, dhi, o));
+    const double spread = __hiloint2double(dhi + 1, 0);
     double c[MFW];
 #pragma unroll
-    for (int j = 0; j < MFW; j++) c[j] = active ? kc[j] : 0.0;
+    for (int j = 0; j < MFW; j++) c[j] = kc[j];
 #pragma unroll
     for (int j = 0; j < 17; j++) v[j] = dsub(v[j], mn);   // delta = raw - minsignal (T2:159), shared by both evaluations
+    const int nvalid = active ? min(7, max(0, T - MFRIGHT - MFLEFT - base)) : 0;   // outputs o < nvalid are stored
     double F[7];
     double fmin_ = 1.0e300;
-    bool valid[7];
 #pragma unroll
     for (int o = 0; o < 7; o++) {
         double a = 0.0;
 #pragma unroll
         for (int jt = 0; jt < MFW; jt++) a = __fma_rn(v[o + jt], c[MFW - 1 - jt], a);
         F[o] = a;
-        valid[o] = active && (MFLEFT + base + o < T - MFRIGHT);
-        if (valid[o]) fmin_ = fmin(fmin_, a);
+        if (o < nvalid) fmin_ = dmin2(fmin_, a);
     }
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) fmin_ = fmin(fmin_, __shfl_xor_sync(0xffffffffu, fmin_, o));
-    const double eps = dmul(dsub(mx, mn), epsf);
+    for (int o = 8; o > 0; o >>= 1) fmin_ = dmin2(fmin_, __shfl_xor_sync(FULL, fmin_, o));
+    const double eps = dmul(spread, epsf);
     const double thr = dadd(fmin_, dmul(2.5, eps));
     // exact values of the candidates for the minimum; the reference's mfmin starts at 1e6 (T2:148).  A candidate
     // is evaluated by its half-warp together: lane jt computes the term of tap jt, then the 11 terms are summed
     // in tap order (the reference's order) -- a 90-cycle chain instead of the 700 of a single lane.
-    double E[7];
     double emin = 1.0e6;
-    bool cand[7];
-    const int half = lane_in_warp & 16;
-    const double ktap = (active && hl < MFW) ? kern[MFW - 1 - hl] : 0.0;
+    unsigned candmask = 0;   // bit o: output o of this lane was evaluated exactly (value in F[o])
+    const double ktap = (hl < MFW) ? kern[MFW - 1 - hl] : 0.0;
 #pragma unroll
     for (int o = 0; o < 7; o++) {
-        cand[o] = valid[o] && F[o] <= thr;
-        E[o] = 0.0;
-        unsigned mh = (__ballot_sync(0xffffffffu, cand[o]) >> half) & 0xffffu;
-        while (__any_sync(0xffffffffu, mh != 0)) {
+        const bool cand = o < nvalid && F[o] <= thr;
+        unsigned mh = (__ballot_sync(FULL, cand) >> half) & 0xffffu;
+        while (__any_sync(FULL, mh != 0)) {
             const int L = mh ? (__ffs(mh) - 1) : 0;
             const int it = MFLEFT + 7 * L + o;
             double term = 0.0;
-            if (mh && hl < MFW) {
+            if (hl < MFW) {
                 const double delta = dsub(s[it + hl - MFLEFT], mn);                 // T2:159
                 term = div_by_recip(dmul(delta, ktap), mfint, mfrecip);             // T2:160-161
             }
             double a = 0.0;
 #pragma unroll
-            for (int jt = 0; jt < MFW; jt++) a = dadd(a, __shfl_sync(0xffffffffu, term, half + jt));
-            if (mh && hl == L) { E[o] = a; emin = fmin(emin, a); }
+            for (int jt = 0; jt < MFW; jt++) a = dadd(a, __shfl_sync(FULL, term, half + jt));
+            if (mh && hl == L) { F[o] = a; candmask |= 1u << o; emin = dmin2(emin, a); }
             mh &= mh - 1;
         }
     }
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) emin = fmin(emin, __shfl_xor_sync(0xffffffffu, emin, o));
+    for (int o = 8; o > 0; o >>= 1) emin = dmin2(emin, __shfl_xor_sync(FULL, emin, o));
     if (!active) return;
     if (hl == 0 && minsig_out) *minsig_out = mn;
     if (mf_out) {
+        // one eta for the whole block: |w| <= |F| + |Emin| <= 2 spread sum|c| = 2^48 eps, so 2^-49 |w| <= eps / 2
+        const double eta = dmul(2.5, eps);
 #pragma unroll
         for (int o = 0; o < 7; o++) {
-            if (!valid[o]) continue;
-            const int it = MFLEFT + base + o;
-            float out;
-            if (cand[o]) {
-                out = (float)dsub(E[o], emin);                                   // T2:170, TH1F float storage T2:178
-            } else {
-                const double w = dsub(F[o], emin);
-                const double eta = __fma_rn(fabs(w), 0x1p-49, dmul(2.0, eps));
-                const float lo = (float)dsub(w, eta), hi = (float)dadd(w, eta);
-                out = lo;
-                if (lo != hi) out = (float)dsub(mf_exact_output(s, it, mn, kern, mfint, mfrecip), emin);
+            if (o < nvalid) {
+                const int it = MFLEFT + base + o;
+                const double w = dsub(F[o], emin);                  // exact value for a candidate: T2:170
+                float out = (float)w;                                // TH1F float storage T2:178
+                if (!((candmask >> o) & 1u)) {
+                    const float lo = (float)dsub(w, eta), hi = (float)dadd(w, eta);
+                    if (lo != hi) out = (float)dsub(mf_exact_output(s, it, mn, kern, mfint, mfrecip), emin);
+                }
+                mf_out[it] = out;
             }
-            mf_out[it] = out;
         }
         if (hl == 0) {
 #pragma unroll
@@ -165,12 +177,17 @@ front_kernel(const double *__restrict__ signal, const int32_t *__restrict__ pres
     double *ring = reinterpret_cast<double *>(smem_raw);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)FRONT_RING * ROW_BYTES);
     uint8_t *pres1 = smem_raw + (size_t)FRONT_RING * ROW_BYTES + 64;
+    // a trace of zeros stands in for every neighbour that is outside the grid or absent: sum + 0.0 is the identity,
+    // so the 3x3 sums need no predicates
+    double *zrow = reinterpret_cast<double *>(smem_raw + (size_t)FRONT_RING * ROW_BYTES + 64 + 1088 + 16);
+    const int ZOFF = (int)(zrow - ring);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
         for (int i = 0; i < FRONT_RING; i++) mbar_init(&bars[i], 1);
         mbar_fence_init();
     }
+    for (int i = tid; i < 128; i += FRONT_THREADS) zrow[i] = 0.0;
     __syncthreads();
     uint32_t phase_bits = 0;  // parity per slot (bit i)
 
@@ -199,10 +216,9 @@ front_kernel(const double *__restrict__ signal, const int32_t *__restrict__ pres
                 phase_bits ^= (1u << slot);
                 waited++;
             }
-            const double *rowp[3];
-            rowp[0] = (r > 0) ? ring + (size_t)((r - 1) % FRONT_RING) * ROW_DOUBLES : nullptr;
-            rowp[1] = ring + (size_t)(r % FRONT_RING) * ROW_DOUBLES;
-            rowp[2] = (r + 1 < NLIN) ? ring + (size_t)((r + 1) % FRONT_RING) * ROW_DOUBLES : nullptr;
+            // ring offsets (in doubles) of the rows r-1, r, r+1
+            const int ro[3] = {((r + FRONT_RING - 1) % FRONT_RING) * ROW_DOUBLES, (r % FRONT_RING) * ROW_DOUBLES,
+                               ((r + 1) % FRONT_RING) * ROW_DOUBLES};
 
             if (do_mf) {
                 // 30 half-warp tasks: warp w takes block pairs {2w', 2w'+1}
@@ -210,13 +226,18 @@ front_kernel(const double *__restrict__ signal, const int32_t *__restrict__ pres
                     const int col = 2 * pair + (lane >> 4);
                     const int bn = r * NCOL + col;
                     const bool active = (pres1[bn] & 2) != 0;
+                    if (!__any_sync(0xffffffffu, active)) continue;
                     const size_t gi = (size_t)e * B + bn;
-                    mf_block_halfwarp(rowp[1] + col * T, lane, active, cal.mfyref + (size_t)bn * MFW,
+                    mf_block_halfwarp(ring + ro[1] + col * T, lane, active, cal.mfyref + (size_t)bn * MFW,
                                       cal.mfc + (size_t)bn * MFW, cal.mfint[bn], cal.mfrecip[bn], cal.mfepsf[bn],
                                       mf_out ? mf_out + gi * T : nullptr, minsig_out ? minsig_out + gi : nullptr);
                 }
             }
-            for (int col = warp; col < NCOL; col += FRONT_WARPS) {
+            // 30 warp tasks.  The matched filter gave warps 0-6 two block pairs and warp 7 one, so the columns are dealt
+            // 4-4-4-4-3-3-3-5: every warp ends the row with about the same number of instructions
+            const int c_first = (warp < 4) ? 4 * warp : ((warp < 7) ? 16 + 3 * (warp - 4) : 25);
+            const int c_count = (warp < 4) ? 4 : ((warp < 7) ? 3 : 5);
+            for (int col = c_first; col < c_first + c_count; col++) {
                 const int bn = r * NCOL + col;
                 const bool present = (pres1[bn] & 2) != 0;
                 bool ok = false;
@@ -224,27 +245,36 @@ front_kernel(const double *__restrict__ signal, const int32_t *__restrict__ pres
                     // neighbour order of T2:247-248; the pres gate (T2:257) uses bit0 only
                     const int dR[8] = {0, 0, +1, -1, +1, +1, -1, -1};
                     const int dC[8] = {+1, -1, 0, 0, +1, -1, +1, -1};
-                    const double *nb[8];
+                    int off[9];
+                    off[0] = ro[1] + col * T + lane;
 #pragma unroll
                     for (int k = 0; k < 8; k++) {
                         const int nr = r + dR[k], nc = col + dC[k];
-                        const bool in = !(nr < 0 || nr >= NLIN || nc < 0 || nc >= NCOL) && (pres1[nr * NCOL + nc] & 1);
-                        nb[k] = in ? rowp[1 + dR[k]] + nc * T : nullptr;
+                        const bool in = (unsigned)nr < (unsigned)NLIN && (unsigned)nc < (unsigned)NCOL &&
+                                        (pres1[min(max(nr, 0), NLIN - 1) * NCOL + min(max(nc, 0), NCOL - 1)] & 1);
+                        off[1 + k] = (in ? ro[1 + dR[k]] + nc * T : ZOFF) + lane;
                     }
-                    const double *self = rowp[1] + col * T;
-                    const double center = dadd(cal.timeref[bn], kp.timerefacc);  // T2:232
-                    const double cw = (double)kp.coinc_width;
+                    // window |it - center| < coinc_width (T2:267) as the integer interval [lo, lo + span], evaluated
+                    // with the reference's own expression on the host (npswf_create)
+                    const int wlo = cal.win_lo[bn];
+                    const unsigned wspan = (unsigned)cal.win_span[bn];
                     double gmin = 1e6, wmax = -1e6;  // T2:238-239
-                    for (int it = lane; it < T; it += 32) {
-                        double sum = self[it];
 #pragma unroll
-                        for (int k = 0; k < 8; k++)
-                            if (nb[k]) sum = dadd(sum, nb[k][it]);
-                        gmin = fmin(gmin, sum);
-                        if (fabs(dsub((double)it, center)) < cw) wmax = fmax(wmax, sum);  // T2:267
+                    for (int i = 0; i < 4; i++) {
+                        const int it = lane + 32 * i;
+                        double sum = ring[off[0] + 32 * i];
+#pragma unroll
+                        for (int k = 1; k < 9; k++) sum = dadd(sum, ring[off[k] + 32 * i]);
+                        if (i < 3 || it < T) {
+                            gmin = dmin2(gmin, sum);
+                            if ((unsigned)(it - wlo) <= wspan) wmax = dmax2(wmax, sum);
+                        }
                     }
-                    gmin = warp_min(gmin);
-                    wmax = warp_max(wmax);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        gmin = dmin2(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
+                        wmax = dmax2(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+                    }
                     ok = dsub(wmax, gmin) > kp.trig_thres;  // T2:277
                 }
                 if (lane == 0 && flags_out)

@@ -681,6 +681,25 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
         if ((rc = dev_upload(h, s, &s.cal.mfint, h->mfint.data(), h->mfint.size()))) return fail(rc);
         if ((rc = dev_upload(h, s, &s.cal.mfrecip, mfrecip.data(), mfrecip.size()))) return fail(rc);
         if ((rc = dev_upload(h, s, &s.cal.mfc, mfc.data(), mfc.size()))) return fail(rc);
+        {   // coincidence window per block: the reference's test |it - center| < coinc_width (T2:232, 267), bin by bin
+            std::vector<int32_t> wlo(B, 1 << 20), wspan(B, 0);
+            for (int b = 0; b < B; b++) {
+                const double center = cal->timeref[b] + h->kp.timerefacc;
+                int lo = -1, hi = -1;
+                bool contiguous = true;
+                for (int it = 0; it < T; it++) {
+                    if (std::fabs((double)it - center) < (double)h->kp.coinc_width) {
+                        if (lo < 0) lo = it;
+                        else if (hi != it - 1) contiguous = false;
+                        hi = it;
+                    }
+                }
+                if (!contiguous) { h->err = "coincidence window is not an interval"; return fail(NPSWF_ERR_CALIB); }
+                if (lo >= 0) { wlo[b] = lo; wspan[b] = hi - lo; }
+            }
+            if ((rc = dev_upload(h, s, &s.cal.win_lo, wlo.data(), wlo.size()))) return fail(rc);
+            if ((rc = dev_upload(h, s, &s.cal.win_span, wspan.data(), wspan.size()))) return fail(rc);
+        }
         if ((rc = dev_upload(h, s, &s.cal.mfepsf, mfepsf.data(), mfepsf.size()))) return fail(rc);
         if ((rc = dev_upload(h, s, &s.cal.timeref, cal->timeref, (size_t)B))) return fail(rc);
         if ((rc = dev_upload(h, s, &s.cal.cortime, cal->cortime, (size_t)B))) return fail(rc);
