@@ -169,6 +169,31 @@ const double *npswf_device_timeref(const npswf_handle *h, int32_t dev_slot);
 int64_t npswf_flatten_event(const int32_t *wfnpulse, const double *wftime_padded, const double *wfampl_padded,
                             double *wftime_flat, double *wfampl_flat, int32_t *block_offset);
 
+/* ---- callers on either side of the hot path ------------------------------------------------------- */
+
+/* analyze's waveform unpack (T2:851-889).  samp = the packed hcana stream NPS.cal.fly.adcSampWaveform of n_events
+ * events, concatenated: event e is samp[offsets[e] .. offsets[e+1]) (its NSampWaveForm words), a list of records
+ * [slot, nsamp, nsamp samples].  Slots 2000/2001 are the scintillator PMs (no block, T2:862-865); a slot outside
+ * [0, 1104) ends the event (T2:867-872); an event with more than 1104*112 words is skipped (T2:830-836).
+ * Out: signal[E][1080][110] (zero-filled, T2:851), pres[E][1080].  Host buffers. */
+int npswf_unpack_batch(npswf_handle *h, int64_t n_events, const double *samp, const int64_t *offsets, double *signal,
+                       int32_t *pres);
+
+/* npswf_analyze_batch fed with the packed stream (what the reference's analyze receives, T2:540): the unpack runs
+ * on the device, so only the words of present blocks cross PCIe.  Outputs as npswf_analyze_batch. */
+int npswf_analyze_batch_packed(npswf_handle *h, int64_t n_events, const double *samp, const int64_t *offsets,
+                               const double *corr_time_HMS, int32_t *wfnpulse, double *wftime, double *wfampl,
+                               double *chi2, double *timewf, double *amplwf, uint8_t *status);
+
+/* Per-event diagnostics that land in the WF tree: ampl[E][1080] = pulse maximum per block (init -100, T2:591,
+ * 1051-1056), enertot[E] = sum of the samples with 30 < it < 109 (T2:1038-1042), integtot[E] = sum of all samples
+ * (T2:1035-1036).  The sums are deterministic and exact on the ADC lattice; any output pointer may be NULL.
+ * _batch: host buffers; _device: resident buffers on device slot dev_slot, asynchronous on `stream`. */
+int npswf_event_diagnostics_batch(npswf_handle *h, int64_t n_events, const double *signal, double *ampl,
+                                  double *enertot, double *integtot);
+int npswf_event_diagnostics_device(npswf_handle *h, int32_t dev_slot, int64_t n_events, const double *d_signal,
+                                   double *d_ampl, double *d_enertot, double *d_integtot, void *stream);
+
 /* Bit-exactness tap: the deterministic exp used by the Markov smoothing kernel, evaluated on
  * the device for n inputs (host buffers). */
 int npswf_debug_exp(npswf_handle *h, int64_t n, const double *x, double *y);

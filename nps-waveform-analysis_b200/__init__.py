@@ -54,7 +54,8 @@ EXPORTS = [
     "npswf_analyze_batch_i16", "npswf_analyze_batch_device", "npswf_sync_device", "npswf_find_pulses_mf_batch",
     "npswf_pass_cluster_threshold_batch", "npswf_fitwf_batch", "npswf_matched_filter_batch",
     "npswf_tspectrum_debug", "npswf_get_mf_calib", "npswf_get_spline", "npswf_device_spline",
-    "npswf_device_timeref", "npswf_flatten_event", "npswf_debug_exp", "npswf_debug_exact_ops", "npswf_debug_fp64_peak", "npswf_set_profiling",
+    "npswf_device_timeref", "npswf_flatten_event", "npswf_debug_exp", "npswf_debug_exact_ops", "npswf_debug_fp64_peak", "npswf_unpack_batch", "npswf_analyze_batch_packed",
+    "npswf_event_diagnostics_batch", "npswf_event_diagnostics_device", "npswf_set_profiling",
     "npswf_get_stage_times",
 ]
 
@@ -251,6 +252,35 @@ class NpsWf:
                                                   _p(o["wfnpulse"]), _p(o["wftime"]), _p(o["wfampl"]), _p(o["chi2"]),
                                                   _p(o["timewf"]), _p(o["amplwf"]), _p(o["status"])))
         return o
+
+    def unpack(self, samp, offsets):
+        """analyze's waveform unpack (T2:851-889) of E packed events -> (signal[E,1080,110], pres[E,1080])."""
+        sp = _c(samp, np.float64).ravel()
+        of = _c(offsets, np.int64).ravel()
+        E = of.size - 1
+        sig = np.zeros((E, NBLOCKS, NTIME)); pres = np.zeros((E, NBLOCKS), np.int32)
+        self._check(lib().npswf_unpack_batch(self.h, C.c_int64(E), _p(sp), _p(of), _p(sig), _p(pres)))
+        return sig, pres
+
+    def analyze_packed(self, samp, offsets, corr_time_HMS, out=None):
+        """analyze() on the packed stream NPS.cal.fly.adcSampWaveform (unpacked on the device)."""
+        sp = _c(samp, np.float64).ravel()
+        of = _c(offsets, np.int64).ravel()
+        E = of.size - 1
+        co = _c(corr_time_HMS, np.float64).reshape(E)
+        o = out if out is not None else self.alloc_outputs(E)
+        self._check(lib().npswf_analyze_batch_packed(self.h, C.c_int64(E), _p(sp), _p(of), _p(co), _p(o["wfnpulse"]),
+                                                     _p(o["wftime"]), _p(o["wfampl"]), _p(o["chi2"]), _p(o["timewf"]),
+                                                     _p(o["amplwf"]), _p(o["status"])))
+        return o
+
+    def event_diagnostics(self, signal):
+        """(ampl[E,1080], enertot[E], integtot[E]) of the WF tree (T2:1026-1056)."""
+        sig = _c(signal, np.float64).reshape(-1, NBLOCKS, NTIME)
+        E = sig.shape[0]
+        ampl = np.zeros((E, NBLOCKS)); et = np.zeros(E); it = np.zeros(E)
+        self._check(lib().npswf_event_diagnostics_batch(self.h, C.c_int64(E), _p(sig), _p(ampl), _p(et), _p(it)))
+        return ampl, et, it
 
     def analyze_device(self, n_events, d_signal, d_pres, d_corr, d_wfnpulse, d_wftime, d_wfampl, d_chi2, d_timewf,
                        d_amplwf, d_status, stream=0, slot=0):

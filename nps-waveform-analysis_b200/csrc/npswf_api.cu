@@ -20,6 +20,7 @@
 #include "kernel_fit.cuh"
 #include "kernel_fit_small.cuh"
 #include "kernel_fit_thread.cuh"
+#include "kernel_aux.cuh"
 
 using namespace npswf;
 
@@ -31,6 +32,9 @@ struct Workspace {  // per (device, pipeline stage) buffers for up to `cap` even
     int64_t cap = 0;
     double *signal = nullptr;
     int16_t *counts = nullptr;
+    double *packed = nullptr;       // packed hcana stream of a chunk (npswf_analyze_batch_packed)
+    long long *poffs = nullptr;     // its event offsets
+    size_t packed_cap = 0;
     int32_t *pres = nullptr;
     double *corr = nullptr;
     float *mf = nullptr;
@@ -441,6 +445,8 @@ struct HostIO {
     const double *signal = nullptr;
     const int16_t *counts = nullptr;
     double lsb = 0;
+    const double *packed = nullptr;       // packed stream + event offsets instead of signal / pres
+    const int64_t *offsets = nullptr;
     const int32_t *pres = nullptr;
     const double *corr = nullptr;
     int32_t *wfnpulse = nullptr;
@@ -471,7 +477,19 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
         const size_t nb = (size_t)n * B, ob = (size_t)e0 * B;
         // upload: the workspace must have been drained by the download of chunk k - 2
         if (k >= 2) CU_TRY(h, cudaStreamWaitEvent(s_in, w.ev_out, 0));
-        if (io.counts) {
+        if (io.packed) {
+            const size_t words = (size_t)(io.offsets[e0 + n] - io.offsets[e0]);
+            if (!w.poffs) {
+                if ((rc = dev_alloc(h, s, &w.poffs, (size_t)w.cap + 1))) return rc;
+            }
+            if (words > w.packed_cap) {   // grows to the largest chunk seen (a full event is 1104 * 112 words)
+                CU_TRY(h, cudaStreamSynchronize(s_cmp));
+                if ((rc = dev_alloc(h, s, &w.packed, words + words / 4 + 1))) return rc;
+                w.packed_cap = words + words / 4 + 1;
+            }
+            CU_TRY(h, cudaMemcpyAsync(w.packed, io.packed + io.offsets[e0], words * sizeof(double), cudaMemcpyHostToDevice, s_in));
+            CU_TRY(h, cudaMemcpyAsync(w.poffs, io.offsets + e0, (size_t)(n + 1) * sizeof(long long), cudaMemcpyHostToDevice, s_in));
+        } else if (io.counts) {
             if (!w.counts) {
                 if ((rc = dev_alloc(h, s, &w.counts, (size_t)w.cap * B * T))) return rc;
             }
@@ -479,13 +497,17 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
         } else {
             CU_TRY(h, cudaMemcpyAsync(w.signal, io.signal + ob * T, nb * T * sizeof(double), cudaMemcpyHostToDevice, s_in));
         }
-        CU_TRY(h, cudaMemcpyAsync(w.pres, io.pres + ob, nb * sizeof(int32_t), cudaMemcpyHostToDevice, s_in));
+        if (!io.packed) CU_TRY(h, cudaMemcpyAsync(w.pres, io.pres + ob, nb * sizeof(int32_t), cudaMemcpyHostToDevice, s_in));
         if (io.corr) CU_TRY(h, cudaMemcpyAsync(w.corr, io.corr + e0, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s_in));
         else CU_TRY(h, cudaMemsetAsync(w.corr, 0, (size_t)n * sizeof(double), s_in));
         CU_TRY(h, cudaEventRecord(w.ev_in, s_in));
         // compute
         CU_TRY(h, cudaStreamWaitEvent(s_cmp, w.ev_in, 0));
-        if (io.counts) {
+        if (io.packed) {
+            unpack_kernel<<<(unsigned)std::min<int64_t>(n, 4 * s.sm_count), UNPACK_THREADS, 0, s_cmp>>>(
+                w.packed, w.poffs, (long long)io.offsets[e0], n, w.signal, w.pres);
+            CU_TRY(h, cudaGetLastError());
+        } else if (io.counts) {
             const long long tot = (long long)nb * T;
             widen_counts_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s_cmp>>>(w.counts, w.signal, io.lsb, tot);
             CU_TRY(h, cudaGetLastError());
@@ -890,6 +912,95 @@ int npswf_analyze_batch_i16(npswf_handle *h, int64_t n_events, const int16_t *co
     if (rc) return rc;
     h->host_ctr.n_events += n_events;
     h->host_ctr.n_block_waveforms += n_events * B;
+    return 0;
+}
+
+int npswf_analyze_batch_packed(npswf_handle *h, int64_t n_events, const double *samp, const int64_t *offsets,
+                               const double *corr_time_HMS, int32_t *wfnpulse, double *wftime, double *wfampl, double *chi2,
+                               double *timewf, double *amplwf, uint8_t *status)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (n_events < 0 || (n_events > 0 && (!samp || !offsets))) {
+        h->err = "npswf_analyze_batch_packed: bad arguments";
+        return NPSWF_ERR_ARG;
+    }
+    if (n_events == 0) return 0;
+    HostIO io;
+    io.packed = samp; io.offsets = offsets; io.corr = corr_time_HMS; io.wfnpulse = wfnpulse;
+    io.wftime = wftime; io.wfampl = wfampl; io.chi2 = chi2; io.timewf = timewf; io.amplwf = amplwf; io.status = status;
+    rc = for_each_slot_range(h, n_events, [&](int d, int64_t lo, int64_t hi) { return analyze_range(h, d, lo, hi, io); });
+    if (rc) return rc;
+    h->host_ctr.n_events += n_events;
+    h->host_ctr.n_block_waveforms += n_events * B;
+    return 0;
+}
+
+int npswf_unpack_batch(npswf_handle *h, int64_t n_events, const double *samp, const int64_t *offsets, double *signal,
+                       int32_t *pres)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (n_events < 0 || (n_events > 0 && (!samp || !offsets || !signal || !pres))) return NPSWF_ERR_ARG;
+    if (n_events == 0) return 0;
+    DevSlot &s = h->slots[0];
+    CU_TRY(h, cudaSetDevice(s.device));
+    const size_t words = (size_t)(offsets[n_events] - offsets[0]);
+    double *d_s = nullptr, *d_sig = nullptr;
+    long long *d_o = nullptr;
+    int32_t *d_p = nullptr;
+    CU_TRY(h, cudaMalloc(&d_s, std::max<size_t>(words, 1) * sizeof(double)));
+    CU_TRY(h, cudaMalloc(&d_o, (size_t)(n_events + 1) * sizeof(long long)));
+    CU_TRY(h, cudaMalloc(&d_sig, (size_t)n_events * B * T * sizeof(double)));
+    CU_TRY(h, cudaMalloc(&d_p, (size_t)n_events * B * sizeof(int32_t)));
+    CU_TRY(h, cudaMemcpy(d_s, samp + offsets[0], words * sizeof(double), cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(d_o, offsets, (size_t)(n_events + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+    unpack_kernel<<<(unsigned)std::min<int64_t>(n_events, 4 * s.sm_count), UNPACK_THREADS>>>(d_s, d_o, (long long)offsets[0],
+                                                                                              n_events, d_sig, d_p);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaMemcpy(signal, d_sig, (size_t)n_events * B * T * sizeof(double), cudaMemcpyDeviceToHost));
+    CU_TRY(h, cudaMemcpy(pres, d_p, (size_t)n_events * B * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    cudaFree(d_s); cudaFree(d_o); cudaFree(d_sig); cudaFree(d_p);
+    return 0;
+}
+
+int npswf_event_diagnostics_batch(npswf_handle *h, int64_t n_events, const double *signal, double *ampl, double *enertot,
+                                  double *integtot)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (n_events < 0 || (n_events > 0 && !signal)) return NPSWF_ERR_ARG;
+    if (n_events == 0) return 0;
+    DevSlot &s = h->slots[0];
+    CU_TRY(h, cudaSetDevice(s.device));
+    double *d_sig = nullptr, *d_a = nullptr, *d_e = nullptr, *d_i = nullptr;
+    CU_TRY(h, cudaMalloc(&d_sig, (size_t)n_events * B * T * sizeof(double)));
+    CU_TRY(h, cudaMalloc(&d_a, (size_t)n_events * B * sizeof(double)));
+    CU_TRY(h, cudaMalloc(&d_e, (size_t)n_events * sizeof(double)));
+    CU_TRY(h, cudaMalloc(&d_i, (size_t)n_events * sizeof(double)));
+    CU_TRY(h, cudaMemcpy(d_sig, signal, (size_t)n_events * B * T * sizeof(double), cudaMemcpyHostToDevice));
+    diag_kernel<<<(unsigned)std::min<int64_t>(n_events, 8 * s.sm_count), DIAG_THREADS>>>(d_sig, n_events, d_a, d_e, d_i);
+    CU_TRY(h, cudaGetLastError());
+    if (ampl) CU_TRY(h, cudaMemcpy(ampl, d_a, (size_t)n_events * B * sizeof(double), cudaMemcpyDeviceToHost));
+    if (enertot) CU_TRY(h, cudaMemcpy(enertot, d_e, (size_t)n_events * sizeof(double), cudaMemcpyDeviceToHost));
+    if (integtot) CU_TRY(h, cudaMemcpy(integtot, d_i, (size_t)n_events * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(d_sig); cudaFree(d_a); cudaFree(d_e); cudaFree(d_i);
+    return 0;
+}
+
+int npswf_event_diagnostics_device(npswf_handle *h, int32_t dev_slot, int64_t n_events, const double *d_signal, double *d_ampl,
+                                   double *d_enertot, double *d_integtot, void *stream)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (dev_slot < 0 || dev_slot >= (int)h->slots.size() || n_events < 0 || !d_signal) return NPSWF_ERR_ARG;
+    if (n_events == 0) return 0;
+    DevSlot &s = h->slots[dev_slot];
+    CU_TRY(h, cudaSetDevice(s.device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s.own_stream;
+    diag_kernel<<<(unsigned)std::min<int64_t>(n_events, 8 * s.sm_count), DIAG_THREADS, 0, st>>>(d_signal, n_events, d_ampl,
+                                                                                               d_enertot, d_integtot);
+    CU_TRY(h, cudaGetLastError());
     return 0;
 }
 

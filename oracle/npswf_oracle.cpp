@@ -464,6 +464,61 @@ extern "C" int oracle_fitwf(const OracleHandle *h, int bn, const double *sig, in
     return fitwf_impl(h, bn, sig, npulse, corr_time_HMS, wftime, wfampl, chi2, ncalls, raw_params);
 }
 
+// Waveform unpack of analyze (/root/reference/TEST_2.C:830-889): packed stream [slot, nsamp, samples...] ->
+// signal[1080*110] (zero-filled), pres[1080], minsignal[1080] (init 1e6).  Returns the number of records read.
+// Deviations, all marked "do not replicate" in SURVEY.md App. B: pres[] is only written for bloc < 1080 (the
+// reference writes past its 1080-entry vector for the 24 non-block slots); a sample index >= 110 is dropped instead
+// of spilling into the next block; reads never go past n_words.
+extern "C" int oracle_unpack_event(const double *samp, int64_t n_words, double *signal, int32_t *pres, double *minsignal)
+{
+    const int nslots = 1104;                       // T2:355
+    const int64_t Ndata = (int64_t)nslots * (T + 1 + 1);   // T2:356
+    for (int i = 0; i < B * T; i++) signal[i] = 0.;          // T2:851
+    for (int i = 0; i < B; i++) { pres[i] = 0; if (minsignal) minsignal[i] = 1.0e6; }   // T2:548, 550
+    if (n_words > Ndata) return 0;                 // T2:830-836: the event is not processed
+    int64_t ns = 0;
+    int nrec = 0;
+    while (ns + 1 < n_words) {                     // T2:855 (a header is two words)
+        double bloc = samp[ns]; ns++;
+        const int nsamp = (int)samp[ns]; ns++;
+        if (bloc == 2000) bloc = 1080;             // T2:862-865
+        if (bloc == 2001) bloc = 1081;
+        if (bloc < 0 || bloc > nslots - 0.5) break;   // T2:867-872
+        const int b = (int)bloc;
+        if (b < B) pres[b] = 1;                    // T2:877 (bounded, see above)
+        for (int it = 0; it < nsamp; it++) {       // T2:879-887
+            if (b < B && it < T && ns < n_words) {
+                signal[b * T + it] = samp[ns];
+                if (minsignal) minsignal[b] = std::min(minsignal[b], signal[b * T + it]);
+            }
+            ns++;
+        }
+        nrec++;
+    }
+    return nrec;
+}
+
+// Per-event diagnostics that land in the WF tree (T2:1026-1056): ampl[i] = pulse maximum (init -100, T2:591/845),
+// integtot = sum of all samples, enertot = sum over the cosmic window 30 < it < 109, both in the reference's
+// serial order (block-major).
+extern "C" void oracle_event_diagnostics(const double *signal, double *ampl, double *enertot, double *integtot)
+{
+    double et = 0., it_ = 0.;
+    const int binmin = 30, binmax = 109;           // T2:1029-1030
+    for (int i = 0; i < B; i++) {
+        double sigmax = -100.;
+        ampl[i] = -100.;
+        for (int it = 0; it < T; it++) {
+            const double v = signal[i * T + it];
+            it_ += v;                               // T2:1036
+            if (it > binmin && it < binmax) et += v;   // T2:1038-1042
+            if (v > sigmax) { sigmax = v; ampl[i] = v; }   // T2:1051-1056
+        }
+    }
+    *enertot = et;
+    *integtot = it_;
+}
+
 extern "C" int oracle_analyze_batch(const OracleHandle *h, int64_t n_events, const double *signal, const int32_t *pres,
                                     const double *corr_time_HMS, int32_t *wfnpulse, double *wftime, double *wfampl,
                                     double *chi2, double *timewf, double *amplwf, uint8_t *status, int32_t *ncalls,

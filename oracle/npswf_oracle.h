@@ -93,6 +93,11 @@ int oracle_analyze_batch(const OracleHandle *h, int64_t n_events, const double *
                          uint8_t *status /*[E][B]*/, int32_t *ncalls /*[E][B] or NULL*/, int n_threads);
 
 /* TSpectrum restatement (tspectrum.cpp) */
+/* callers on either side of the hot path: waveform unpack T2:830-889, diagnostics T2:1026-1056 */
+int oracle_unpack_event(const double *samp, int64_t n_words, double *signal /*[B*T]*/, int32_t *pres /*[B]*/,
+                        double *minsignal /*[B] or NULL*/);
+void oracle_event_diagnostics(const double *signal /*[B*T]*/, double *ampl /*[B]*/, double *enertot, double *integtot);
+
 int oracle_search_highres(const double *source, int ssize, double sigma, double threshold, int decon_iterations,
                           int aver_window, int max_peaks, double *pos_x, double *smoothed_out, double *decon_out,
                           int use_libm_exp);

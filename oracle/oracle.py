@@ -97,6 +97,24 @@ def tspectrum_search(hist, sigma=2.0, threshold=0.02, max_peaks=12, libm_exp=Fal
 _FCN = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.c_void_p)
 
 
+def unpack_event(samp):
+    """analyze's waveform unpack (T2:830-889) of one event's packed stream -> (signal[1080,110], pres[1080], minsignal[1080])."""
+    L = lib()
+    sp = _c(samp, np.float64).ravel()
+    sig = np.zeros((NBLOCKS, NTIME)); pres = np.zeros(NBLOCKS, np.int32); mn = np.zeros(NBLOCKS)
+    L.oracle_unpack_event(_p(sp), C.c_int64(sp.size), _p(sig), _p(pres), _p(mn))
+    return sig, pres, mn
+
+
+def event_diagnostics(signal_event):
+    """(ampl[1080], enertot, integtot) of one event (T2:1026-1056)."""
+    L = lib()
+    sig = _c(signal_event, np.float64).reshape(NBLOCKS, NTIME)
+    ampl = np.zeros(NBLOCKS); et = C.c_double(0.0); it = C.c_double(0.0)
+    L.oracle_event_diagnostics(_p(sig), _p(ampl), C.byref(et), C.byref(it))
+    return ampl, float(et.value), float(it.value)
+
+
 def migrad(fcn, start, step, strategy=1, maxfcn=0, tolerance=0.01):
     """Minuit2 Migrad restatement on a Python chi2 callable (unit tests)."""
     L = lib()

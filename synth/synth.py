@@ -118,3 +118,26 @@ def generate_device(params, d_spline, d_timeref, d_kappa, event0, n_events, d_si
                                           C.c_void_p(d_corr), C.c_void_p(stream))
     if rc != 0:
         raise RuntimeError("synth_generate_device: CUDA error %d" % rc)
+
+
+def pack_events(signal, pres, seed=0, scintillators=True):
+    """The packed hcana stream NPS.cal.fly.adcSampWaveform (T2:855-889) of a batch: for every present block a record
+    [slot, 110, samples...] in shuffled slot order, plus the two scintillator PM slots 2000 / 2001 (T2:862-865).
+    Returns (samp, offsets) with event e = samp[offsets[e]:offsets[e+1]]."""
+    rng = np.random.default_rng(seed)
+    sig = np.asarray(signal, np.float64).reshape(-1, NBLOCKS, NTIME)
+    E = sig.shape[0]
+    chunks, offs = [], [0]
+    for e in range(E):
+        slots = np.nonzero(np.asarray(pres)[e] == 1)[0]
+        slots = rng.permutation(slots)
+        rec = np.empty((slots.size, NTIME + 2))
+        rec[:, 0] = slots; rec[:, 1] = NTIME; rec[:, 2:] = sig[e, slots]
+        parts = [rec.ravel()]
+        if scintillators:
+            sc = np.empty((2, NTIME + 2)); sc[:, 0] = (2000, 2001); sc[:, 1] = NTIME; sc[:, 2:] = rng.normal(50, 5, (2, NTIME))
+            parts.insert(rng.integers(0, 2), sc.ravel())
+        ev = np.concatenate(parts)
+        chunks.append(ev)
+        offs.append(offs[-1] + ev.size)
+    return np.concatenate(chunks) if chunks else np.zeros(0), np.array(offs, np.int64)

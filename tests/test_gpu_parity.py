@@ -374,3 +374,70 @@ def test_off_lattice_traces_are_fitted_unrounded(gpu, events):
 def test_fp64_peak_tap(gpu):
     g = gpu.fp64_peak_gflops()
     assert 5e3 < g < 1e5, g   # B200: ~3.4e4 GFLOP/s measured
+
+
+def _malformed_streams(rng):
+    """Packed streams exercising every branch of T2:855-889."""
+    x = np.arange(110.0)
+    def rec(slot, n, vals=None):
+        v = rng.normal(0, 1, n) if vals is None else np.asarray(vals, float)
+        return np.concatenate([[slot, n], v])
+    evs = []
+    evs.append(np.concatenate([rec(3, 110), rec(2000, 110), rec(1079, 110), rec(2001, 110), rec(0, 110)]))      # scintillators
+    evs.append(np.concatenate([rec(5, 110), rec(1104, 110), rec(6, 110)]))                                      # bad slot ends the event
+    evs.append(np.concatenate([rec(5, 110), rec(-1, 110), rec(6, 110)]))                                        # negative slot
+    evs.append(np.concatenate([rec(7, 110, x), rec(8, 110), rec(7, 110, -x)]))                                  # repeated slot: last wins
+    evs.append(np.concatenate([rec(7, 110, x), rec(7, 40, -x[:40]), rec(9, 110)]))                              # repeated, shorter
+    evs.append(np.concatenate([rec(10, 60), rec(11, 110), rec(12, 0), rec(13, 110)]))                           # nsamp != 110
+    evs.append(np.concatenate([rec(1090, 110), rec(20, 110)]))                                                   # non-block slot
+    evs.append(np.concatenate([rec(30, 110), rec(31, 110)])[:-37])                                               # truncated
+    evs.append(np.zeros(0))                                                                                      # empty
+    evs.append(np.concatenate([rec(s, 110) for s in range(1104)] + [rec(2000, 110)]))                            # > 1104*112 words: skipped
+    evs.append(np.concatenate([rec(s, 110) for s in rng.permutation(1080)]))                                     # full event
+    offs = np.concatenate([[0], np.cumsum([e.size for e in evs])]).astype(np.int64)
+    return np.concatenate(evs), offs
+
+
+def test_unpack_exact(gpu, events):
+    """Waveform unpack (T2:851-889) on the device vs the oracle: well-formed shuffled streams and malformed ones."""
+    ev = events[2]
+    samp, offs = synth.pack_events(ev["signal"], ev["pres"], seed=5)
+    sig, pres = gpu.unpack(samp, offs)
+    assert np.array_equal(pres, ev["pres"])
+    assert np.array_equal(sig, np.where(ev["pres"][..., None] == 1, ev["signal"], 0.0))
+    samp, offs = _malformed_streams(np.random.default_rng(9))
+    sig, pres = gpu.unpack(samp, offs)
+    for e in range(offs.size - 1):
+        rs, rp, _ = oracle.unpack_event(samp[offs[e]:offs[e + 1]])
+        assert np.array_equal(pres[e], rp), e
+        assert np.array_equal(sig[e], rs), e
+    assert pres[9].sum() == 0 and pres[10].sum() == 1080 and pres[1].sum() == 1 and pres[6].sum() == 1
+
+
+def test_analyze_packed_equals_analyze(gpu, events):
+    ev = events[2]
+    samp, offs = synth.pack_events(ev["signal"], ev["pres"], seed=6)
+    a = gpu.analyze(np.where(ev["pres"][..., None] == 1, ev["signal"], 0.0), ev["pres"], ev["corr_time_HMS"])
+    b = gpu.analyze_packed(samp, offs, ev["corr_time_HMS"])
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_event_diagnostics(gpu, events):
+    """ampl / enertot / integtot of the WF tree (T2:1026-1056): ampl exact, the sums exact on the ADC lattice and
+    within 1e-12 relative for arbitrary doubles."""
+    ev = events[2]
+    ampl, et, it = gpu.event_diagnostics(ev["signal"])
+    for e in range(ev["signal"].shape[0]):
+        ra, re, ri = oracle.event_diagnostics(ev["signal"][e])
+        assert np.array_equal(ampl[e], ra) and et[e] == re and it[e] == ri
+    rng = np.random.default_rng(4)
+    sig = rng.normal(0, 50, (2, 1080, 110))
+    sig[0, 5] = -500.0                      # below the -100 initial value of sigmax
+    ampl, et, it = gpu.event_diagnostics(sig)
+    for e in range(2):
+        ra, re, ri = oracle.event_diagnostics(sig[e])
+        assert np.array_equal(ampl[e], ra)
+        scale = np.abs(sig[e]).sum()
+        assert abs(et[e] - re) <= 1e-12 * scale and abs(it[e] - ri) <= 1e-12 * scale
+    assert ampl[0, 5] == -100.0

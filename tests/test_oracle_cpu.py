@@ -205,3 +205,26 @@ def test_output_state_table(orc, events):
     assert (r["chi2"][0][fitted] > 0).all()
     pad = r["wftime"][0][np.arange(12)[None, :] >= n[:, None]]
     assert (pad == -999).all()
+
+
+def test_unpack_and_diagnostics_restatement(events):
+    """oracle.unpack_event / event_diagnostics (T2:830-889, 1026-1056): round trip of synth.pack_events, the
+    scintillator renumbering, the break on a bad slot and the closed forms of the diagnostics."""
+    import synth
+    ev = events[2]
+    samp, offs = synth.pack_events(ev["signal"], ev["pres"], seed=1)
+    for e in range(ev["signal"].shape[0]):
+        sig, pres, mn = oracle.unpack_event(samp[offs[e]:offs[e + 1]])
+        assert np.array_equal(pres, ev["pres"][e])
+        on = ev["pres"][e] == 1
+        assert np.array_equal(sig[on], ev["signal"][e][on]) and (sig[~on] == 0).all()
+        assert np.array_equal(mn[on], ev["signal"][e][on].min(axis=1)) and (mn[~on] == 1e6).all()
+        ampl, et, it = oracle.event_diagnostics(sig)
+        assert np.array_equal(ampl, np.maximum(sig.max(axis=1), -100.0))
+        assert abs(it - sig.sum()) < 1e-6 and abs(et - sig[:, 31:109].sum()) < 1e-6
+    bad = np.concatenate([[4, 110], np.ones(110), [1104, 110], np.ones(110), [5, 110], np.ones(110)])
+    sig, pres, _ = oracle.unpack_event(bad)
+    assert pres.sum() == 1 and pres[4] == 1
+    big = np.zeros(1104 * 112 + 1)
+    sig, pres, _ = oracle.unpack_event(big)
+    assert pres.sum() == 0
