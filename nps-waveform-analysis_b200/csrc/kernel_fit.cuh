@@ -32,6 +32,7 @@ struct FitSmem {
     double dp[PMAX];
     double par[PMAX];
     double trial[PMAX];
+    double s2[PMAX / 2];             // second-order term of the exact half-Hessian on (t_n, t_n): -sum r w A_n S''
 };
 
 __device__ __forceinline__ int tri(int a, int b) { return a * (a + 1) / 2 + b; }  // a >= b
@@ -76,14 +77,23 @@ __device__ __forceinline__ double eval_points(const double *__restrict__ par, in
 
 // Cholesky solve of (JtJ + lambda*diag) dp = Jtr, executed redundantly by every lane on the
 // warp's shared copy (identical values, benign same-value stores).  Returns false if not PD.
+// With `newton` the matrix is the exact half-Hessian (see NormalEq in kernel_fit_small.cuh): the (t_n, t_n) term
+// comes from sm->s2, the (A_n, t_n) term sum r w S' equals -Jtr[t_n] / A_n.
 template <int PMAX>
-__device__ __forceinline__ bool damped_solve(FitSmem<PMAX> *sm, int P, double lambda)
+__device__ __forceinline__ bool damped_solve(FitSmem<PMAX> *sm, int P, double lambda, bool newton)
 {
     double *A = sm->A;
     for (int a = 0; a < P; a++)
         for (int b = 0; b <= a; b++) {
             double v = sm->JtJ[tri(a, b)];
-            if (a == b) v += lambda * (v + 1e-12);
+            if (newton) {
+                if (a == b && (a & 1)) v += sm->s2[(a - 1) / 2];
+                if (a == b + 1 && (b & 1)) {
+                    const double An = sm->par[a];
+                    if (An != 0.0) v -= sm->Jtr[b] / An;
+                }
+            }
+            if (a == b) v += lambda * (fabs(v) + 1e-12);
             A[tri(a, b)] = v;
         }
     __syncwarp();
@@ -128,7 +138,7 @@ __device__ __forceinline__ LmOutcome lm_warp(FitSmem<PMAX> *sm, int N, int P, in
 {
     double lambda = lambda0;
     double chi2 = eval_points<PMAX, false>(sm->par, N, P, lane, y, w, spl, sm);
-    bool converged = false;
+    bool converged = false, newton = false;   // exact-Hessian steps once an accepted step gains < 5 %
     int it = 0;
     const int ntri = P * (P + 1) / 2;
     for (; it < max_iter; it++) {
@@ -136,9 +146,23 @@ __device__ __forceinline__ LmOutcome lm_warp(FitSmem<PMAX> *sm, int N, int P, in
         eval_points<PMAX, true>(sm->par, N, P, lane, y, w, spl, sm);
         __syncwarp();
         // normal equations: entries spread over lanes
-        for (int idx = lane; idx < ntri + P; idx += 32) {
+        for (int idx = lane; idx < ntri + P + N; idx += 32) {
             double s = 0;
-            if (idx < ntri) {
+            if (idx >= ntri + P) {
+                // s2[n] = -A_n sum_k r_k w_k S''(x_k - t_n): the weights are column 0 of J
+                const int n = idx - ntri - P;
+                const double tn = sm->par[1 + 2 * n], an = sm->par[2 + 2 * n];
+                for (int k = 0; k < NFIT; k++) {
+                    const double d = (double)(MFSTART + k) - tn;
+                    if (d > 1.0 && d < (double)(T - 1)) {
+                        const int i = (int)d;
+                        const double f = d - (double)i;
+                        const double2 q23 = *reinterpret_cast<const double2 *>(spl + 4 * i + 2);
+                        s += sm->r[k] * sm->J[k * P] * (2.0 * q23.x + 6.0 * f * q23.y);
+                    }
+                }
+                sm->s2[n] = -an * s;
+            } else if (idx < ntri) {
                 int a = 0;
                 while (tri(a + 1, 0) <= idx) a++;
                 const int b = idx - tri(a, 0);
@@ -153,9 +177,14 @@ __device__ __forceinline__ LmOutcome lm_warp(FitSmem<PMAX> *sm, int N, int P, in
         __syncwarp();
         bool accepted = false;
         for (int tries = 0; tries < 30 && !accepted; tries++) {
-            const bool pd = damped_solve<PMAX>(sm, P, lambda);
+            const bool pd = damped_solve<PMAX>(sm, P, lambda, newton);
             __syncwarp();
             if (!pd) { lambda = fmax(lambda * 10, 1e-6); continue; }
+            if (lambda <= 1e-2) {   // predicted-decrease stop (see fit_thread_kernel)
+                double pred2 = 0;
+                for (int a = 0; a < P; a++) pred2 += sm->Jtr[a] * sm->dp[a];
+                if (2.0 * pred2 < rel_tol * (fabs(chi2) + 1e-30)) { converged = true; accepted = true; break; }
+            }
             if (lane < P) sm->trial[lane] = sm->par[lane] + sm->dp[lane];
             __syncwarp();
             const double c2 = eval_points<PMAX, false>(sm->trial, N, P, lane, y, w, spl, sm);
@@ -165,6 +194,7 @@ __device__ __forceinline__ LmOutcome lm_warp(FitSmem<PMAX> *sm, int N, int P, in
                 chi2 = c2;
                 lambda = fmax(lambda * 0.2, 1e-12);
                 accepted = true;
+                if (rel < 0.05) newton = true;
                 if (rel < rel_tol) converged = true;
             } else {
                 lambda = fmax(lambda * 10, 1e-6);

@@ -321,11 +321,13 @@ fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
         if (handoff) {   // continuation record: fit_small_kernel re-evaluates at par and carries on
             const int idx = atomicAdd(cont_count, 1);
             cont_list[idx] = (int)item;
-            double *cs = cont_state + (size_t)idx * FT_CONT_STRIDE;
+            if (cont_state) {   // (N >= 4: the warp-per-fit kernel restarts the fit from its seeds)
+                double *cs = cont_state + (size_t)idx * FT_CONT_STRIDE;
 #pragma unroll
-            for (int i = 0; i < P; i++) cs[i] = par[i];
-            cs[P] = lambda;
-            cs[P + 1] = (double)((iters << 7) | (rejects << 1) | (newton ? 1 : 0));
+                for (int i = 0; i < P; i++) cs[i < FT_CONT_STRIDE - 2 ? i : 0] = par[i];
+                cs[P < FT_CONT_STRIDE - 2 ? P : 0] = lambda;
+                cs[P + 1 < FT_CONT_STRIDE ? P + 1 : 0] = (double)((iters << 7) | (rejects << 1) | (newton ? 1 : 0));
+            }
             has_job = false;
         }
         // ---- write back converged fits (T2:796-827)

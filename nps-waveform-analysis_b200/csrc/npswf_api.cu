@@ -70,7 +70,7 @@ struct DevSlot {
     bool fit_concurrent = true;  // env NPSWF_FIT_CONCURRENT=0 serialises the fit kernels on the caller's stream
     bool fit2_group16 = false;  // development knob (env NPSWF_FIT2_GROUP=16)
     bool fit_thread = true;     // thread-per-fit kernels for N = 1, 2 (env NPSWF_FIT_THREAD=0 selects the sub-warp kernels)
-    int occ_fit_thread[4] = {0, 2, 2, 2};
+    int occ_fit_thread[5] = {0, 2, 2, 2, 2};   // [4]: N = 4..6
     int fit_thread_maxocc = 0;  // env NPSWF_FIT_THREAD_OCC: cap on resident CTAs per SM (fewer CTAs leave more L1)
     int occ_front = 2, occ_search = 4, occ_fit_big = 1, occ_fit_small[4] = {0, 4, 4, 2};  // resident CTAs per SM
     std::vector<cudaEvent_t> prof_events;  // 4 per profiled chunk: start, after front, after search, after fits
@@ -183,7 +183,7 @@ int alloc_workspace(npswf_handle *h, DevSlot &s, Workspace &w, int64_t cap, bool
     if ((rc = dev_alloc(h, s, &w.minsig, nb))) return rc;
     if ((rc = dev_alloc(h, s, &w.flags, nb))) return rc;
     if ((rc = dev_alloc(h, s, &w.fit_count, 64))) return rc;
-    if ((rc = dev_alloc(h, s, &w.cont_list, (size_t)3 * nb))) return rc;
+    if ((rc = dev_alloc(h, s, &w.cont_list, (size_t)6 * nb))) return rc;
     if ((rc = dev_alloc(h, s, &w.cont_state, (size_t)3 * nb * FT_CONT_STRIDE))) return rc;
     if ((rc = dev_alloc(h, s, &w.bucket_count, (size_t)(MAXP + 1) * B))) return rc;
     if ((rc = dev_alloc(h, s, &w.fit_list, (size_t)(MAXP + 1) * nb))) return rc;
@@ -346,6 +346,24 @@ int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, cons
                 fit_small_kernel<3, 16, FS_MINB3><<<s.sm_count * s.occ_fit_small[3], FS_THREADS, 0, st>>>(
                     clist, ccnt, cnext, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, cstate);
             }
+        } else if (N >= 4 && N <= 6 && s.fit_thread) {
+            // thread-per-fit also for 4-6 pulses (the normal equations spill to L1-resident local memory, which is
+            // read once per try); the few fits it hands over are redone from their seeds by the warp-per-fit kernel
+            int *ccnt = w.fit_count + 32 + N;
+            int *clist = w.cont_list + (size_t)(N - 1) * stride;
+            const int tgrid = s.sm_count * s.occ_fit_thread[4];
+            if (N == 4)
+                fit_thread_kernel<4><<<tgrid, FT_THREADS, FT_SMEM, st>>>(list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl,
+                                                                        chi2, timewf, amplwf, status, s.ctr, ccnt, clist, nullptr);
+            else if (N == 5)
+                fit_thread_kernel<5><<<tgrid, FT_THREADS, FT_SMEM, st>>>(list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl,
+                                                                        chi2, timewf, amplwf, status, s.ctr, ccnt, clist, nullptr);
+            else
+                fit_thread_kernel<6><<<tgrid, FT_THREADS, FT_SMEM, st>>>(list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl,
+                                                                        chi2, timewf, amplwf, status, s.ctr, ccnt, clist, nullptr);
+            CU_TRY(h, cudaGetLastError());
+            fit_kernel<25><<<s.sm_count * s.occ_fit_big, FIT_THREADS, sizeof(FitSmem<25>) * FIT_WARPS, st>>>(
+                clist, ccnt, N, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr);
         } else if (N == 1) {
             fit_small_kernel<1, 8, FS_MINB1><<<s.sm_count * s.occ_fit_small[1], FS_THREADS, 0, st>>>(
                 list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr);
@@ -775,6 +793,9 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
         CR(cudaFuncSetAttribute(fit_thread_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
         CR(cudaFuncSetAttribute(fit_thread_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
         CR(cudaFuncSetAttribute(fit_thread_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
+        CR(cudaFuncSetAttribute(fit_thread_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
+        CR(cudaFuncSetAttribute(fit_thread_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
+        CR(cudaFuncSetAttribute(fit_thread_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_thread[3], fit_thread_kernel<3>, FT_THREADS, FT_SMEM));
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_thread[1], fit_thread_kernel<1>, FT_THREADS, FT_SMEM));
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_thread[2], fit_thread_kernel<2>, FT_THREADS, FT_SMEM));
