@@ -162,7 +162,7 @@ fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
                   double *__restrict__ cont_state)
 {
     constexpr int P = 2 * N + 1;
-    constexpr int U = (N == 1) ? 5 : ((N == 2) ? 3 : 1);
+    constexpr int U = (N == 1) ? 5 : 1;
     constexpr double REL_TOL = 1e-9;
     const unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char ft_smem[];
