@@ -386,7 +386,7 @@ def main():
                    "fit_iterations_mean": iters / max(1, fitted), "fallback": n_fb, "retry_ok": n_retry,
                    "l2": "inputs larger than L2: %.2f GB of traces per step, two resident batches alternated" % (E * NB * NT * 8 / 1e9)},
         "clocks": clocks, "e2e": e2e,
-        "gpu_launches": int(args.steps * ((E + h.chunk_events - 1) // h.chunk_events) * 18),
+        "gpu_launches": int(args.steps * ((E + h.chunk_events - 1) // h.chunk_events) * 21),  # front, search, compact, 18 fit kernels per chunk
         "roofline": roofline, "stages": stage_rows,
         "fit_fp64": {"gflops": fit_gflops, "flops_per_iter_model": flops_iter, "fp64_peak_gflops_measured": fp64_peak,
                      "frac_of_fp64_peak": fit_gflops / fp64_peak if fp64_peak > 0 else None,
