@@ -482,10 +482,13 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
     // Host buffers: a three-stage pipeline over the two workspaces -- uploads on their own stream, every kernel on
     // one compute stream (two chunks computing side by side would only fight for shared memory), downloads on a
     // third stream -- so the copy engines of both directions run under the kernels of the neighbouring chunks.
-    // About eight chunks per call (multiples of 148 events, at least 296) keep the uncovered first upload and
+    // Eight to twelve chunks per call (multiples of 148 events, at least 296) keep the uncovered first upload and
     // last download short.
+    // (the binary64 layouts are bound by the upload: more, smaller chunks; the int16 layout by the kernels: fewer, larger)
+    const int64_t target = io.counts ? 8 : 12;
     int64_t chunk = h->chunk;
-    if (hi - lo > 2 * 296) chunk = std::min<int64_t>(h->chunk, std::max<int64_t>(296, ((hi - lo + 8 * 148 - 1) / (8 * 148)) * 148));
+    if (hi - lo > 2 * 296)
+        chunk = std::min<int64_t>(h->chunk, std::max<int64_t>(296, ((hi - lo + target * 148 - 1) / (target * 148)) * 148));
     cudaStream_t s_in = s.copy_in, s_out = s.copy_out, s_cmp = s.ws[0].stream;
     int which = 0;
     int64_t k = 0;

@@ -29,7 +29,7 @@ def main():
         n = min(296, E - 296 * r)
         hs[296 * r:296 * r + n] = base["signal"][:n]; hk[296 * r:296 * r + n] = base["counts"][:n]
         hp[296 * r:296 * r + n] = base["pres"][:n]; hc[296 * r:296 * r + n] = base["corr_time_HMS"][:n]
-    for chunk in (592,):
+    for chunk in (296, 444, 592):
         h = pkg.NpsWf(cal, chunk_events=chunk)
         ho = h.alloc_outputs(E, pinned=True)
         for name, fn in (("f64", lambda: h.analyze(hs, hp, hc, out=ho)), ("i16", lambda: h.analyze_i16(hk, synth.LSB, hp, hc, out=ho))):
