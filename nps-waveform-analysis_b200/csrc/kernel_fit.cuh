@@ -213,8 +213,11 @@ __global__ void __launch_bounds__(FIT_THREADS)
 fit_kernel(const int *__restrict__ job_list, const int *__restrict__ job_count, int N, const double *__restrict__ signal,
            const double *__restrict__ corr_time_HMS, DevCalib cal, KParams kp, double *__restrict__ wftime,
            double *__restrict__ wfampl, double *__restrict__ chi2_out, double *__restrict__ timewf,
-           double *__restrict__ amplwf, uint8_t *__restrict__ status, DeviceCounters *__restrict__ ctr)
+           double *__restrict__ amplwf, uint8_t *__restrict__ status, DeviceCounters *__restrict__ ctr,
+           int first_attempt_done = 0, int first_attempt_iters = 0)
 {
+    // first_attempt_done: the list holds fits whose first attempt was run (and exhausted) by fit_thread_kernel;
+    // only the retry is left to do here
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     FitSmem<PMAX> *sm = reinterpret_cast<FitSmem<PMAX> *>(smem_raw) + warp;
@@ -260,7 +263,8 @@ fit_kernel(const int *__restrict__ job_list, const int *__restrict__ job_count, 
             sm->par[2 + 2 * lane] = seed_a;
         }
         __syncwarp();
-        LmOutcome r = lm_warp<PMAX>(sm, N, P, lane, y, w, spl, kp.fit_max_iter, 1e-3, 1e-9);
+        LmOutcome r = {false, 0.0, first_attempt_iters};
+        if (!first_attempt_done) r = lm_warp<PMAX>(sm, N, P, lane, y, w, spl, kp.fit_max_iter, 1e-3, 1e-9);
         int st = 0;
         int iters = r.iters;
         if (r.ok) st = NPSWF_ST_FIT_OK1;

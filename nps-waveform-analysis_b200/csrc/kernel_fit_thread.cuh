@@ -170,7 +170,9 @@ fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
     float2 *ywwarp = reinterpret_cast<float2 *>(ft_smem + (size_t)warp * FT_WARP_BYTES);   // [90][33] (sample, 1/err)
     const float2 *ywcol = ywwarp + lane;
     const int njobs = *job_count;
-    const int max_tries = kp.fit_thread_tries;
+    // N >= 4 has no sub-warp continuation kernel: the thread runs the whole first attempt (at most fit_max_iter accepted
+    // steps and 30 rejected ones) and hands over only what needs the retry
+    const int max_tries = (N <= 3) ? kp.fit_thread_tries : kp.fit_max_iter + 30;
     unsigned long long c_ok1 = 0, c_it = 0, c_att = 0, c_ev = 0;
 
     bool has_job = false, exhausted = false, fresh = false;

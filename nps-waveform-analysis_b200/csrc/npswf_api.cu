@@ -348,7 +348,7 @@ int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, cons
             }
         } else if (N >= 4 && N <= 6 && s.fit_thread) {
             // thread-per-fit also for 4-6 pulses (the normal equations spill to L1-resident local memory, which is
-            // read once per try); the few fits it hands over are redone from their seeds by the warp-per-fit kernel
+            // read once per try); it runs the whole first attempt, the warp-per-fit kernel the retries
             int *ccnt = w.fit_count + 32 + N;
             int *clist = w.cont_list + (size_t)(N - 1) * stride;
             const int tgrid = s.sm_count * s.occ_fit_thread[4];
@@ -363,7 +363,7 @@ int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, cons
                                                                         chi2, timewf, amplwf, status, s.ctr, ccnt, clist, nullptr);
             CU_TRY(h, cudaGetLastError());
             fit_kernel<25><<<s.sm_count * s.occ_fit_big, FIT_THREADS, sizeof(FitSmem<25>) * FIT_WARPS, st>>>(
-                clist, ccnt, N, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr);
+                clist, ccnt, N, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, 1, h->kp.fit_max_iter);
         } else if (N == 1) {
             fit_small_kernel<1, 8, FS_MINB1><<<s.sm_count * s.occ_fit_small[1], FS_THREADS, 0, st>>>(
                 list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr);
@@ -616,7 +616,7 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
     h->kp.specthres = cfg->specthres; h->kp.mfthres = cfg->mfthres; h->kp.trig_thres = cfg->trig_thres;
     h->kp.dt = cfg->dt; h->kp.timerefacc = cfg->timerefacc; h->kp.coinc_width = cfg->coinc_width;
     h->kp.fit_max_iter = cfg->fit_max_iter > 0 ? cfg->fit_max_iter : 60;
-    h->kp.fit_retry_max_iter = cfg->fit_retry_max_iter > 0 ? cfg->fit_retry_max_iter : 300;
+    h->kp.fit_retry_max_iter = cfg->fit_retry_max_iter > 0 ? cfg->fit_retry_max_iter : 100;
     h->kp.fit_thread_tries = (getenv("NPSWF_FIT_THREAD_TRIES") && atoi(getenv("NPSWF_FIT_THREAD_TRIES")) > 0) ? atoi(getenv("NPSWF_FIT_THREAD_TRIES")) : 20;
     h->chunk = cfg->chunk_events > 0 ? cfg->chunk_events : 1184;
     // ---- derived calibration on the host (T2:440-451 for mfyref/mfint; spline coefficients)
