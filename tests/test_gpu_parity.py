@@ -441,3 +441,19 @@ def test_event_diagnostics(gpu, events):
         scale = np.abs(sig[e]).sum()
         assert abs(et[e] - re) <= 1e-12 * scale and abs(it[e] - ri) <= 1e-12 * scale
     assert ampl[0, 5] == -100.0
+
+
+def test_two_devices_in_one_process_equal_one_device(pkg, calib, spline):
+    """n_devices = 2 (contiguous event ranges, one host thread per device inside the call) gives the same outputs
+    as one device.  Skipped on a single-GPU box."""
+    if pkg.lib().npswf_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    E = 700
+    ev = synth.generate_host(synth.config_params(2, absent_frac=0.02), spline, calib, 90000, E, n_threads=8)
+    one = pkg.NpsWf(calib, devices=[0]).analyze(ev["signal"], ev["pres"], ev["corr_time_HMS"])
+    h2 = pkg.NpsWf(calib, devices=[0, 1])
+    two = h2.analyze(ev["signal"], ev["pres"], ev["corr_time_HMS"])
+    for k in one:
+        assert np.array_equal(one[k], two[k]), k
+    c = h2.counters()
+    assert c["n_events"] == E and c["n_fit_attempted"] == int(((one["status"] & 28) > 0).sum())
