@@ -66,9 +66,7 @@ struct DevSlot {
     cudaStream_t own_stream = nullptr, copy_in = nullptr, copy_out = nullptr;
     cudaStream_t fit_stream[4] = {nullptr, nullptr, nullptr, nullptr};  // N = 1 | N = 2 | N = 3 | N >= 4 run concurrently
     cudaEvent_t fit_fork = nullptr, fit_join[4] = {nullptr, nullptr, nullptr, nullptr}, chunk_join[2] = {nullptr, nullptr};
-    int cont_group = 16;  // lanes per fit of the continuation kernels (env NPSWF_CONT_GROUP)
     bool fit_concurrent = true;  // env NPSWF_FIT_CONCURRENT=0 serialises the fit kernels on the caller's stream
-    bool fit2_group16 = false;  // development knob (env NPSWF_FIT2_GROUP=16)
     bool fit_thread = true;     // thread-per-fit kernels for N = 1, 2 (env NPSWF_FIT_THREAD=0 selects the sub-warp kernels)
     int occ_fit_thread[5] = {0, 2, 2, 2, 2};   // [4]: N = 4..6
     int fit_thread_maxocc = 0;  // env NPSWF_FIT_THREAD_OCC: cap on resident CTAs per SM (fewer CTAs leave more L1)
@@ -366,9 +364,6 @@ int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, cons
                 clist, ccnt, N, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, 1, h->kp.fit_max_iter);
         } else if (N == 1) {
             fit_small_kernel<1, 8, FS_MINB1><<<s.sm_count * s.occ_fit_small[1], FS_THREADS, 0, st>>>(
-                list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr);
-        } else if (N == 2 && s.fit2_group16) {
-            fit_small_kernel<2, 16, 3><<<s.sm_count * s.occ_fit_small[2], FS_THREADS, 0, st>>>(
                 list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr);
         } else if (N == 2) {
             fit_small_kernel<2, 8, FS_MINB2><<<s.sm_count * s.occ_fit_small[2], FS_THREADS, 0, st>>>(
@@ -773,7 +768,6 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
         CR(cudaStreamCreateWithFlags(&s.own_stream, cudaStreamNonBlocking));
         CR(cudaStreamCreateWithFlags(&s.copy_in, cudaStreamNonBlocking));
         CR(cudaStreamCreateWithFlags(&s.copy_out, cudaStreamNonBlocking));
-        if (getenv("NPSWF_CONT_GROUP")) s.cont_group = atoi(getenv("NPSWF_CONT_GROUP"));
         s.fit_concurrent = !(getenv("NPSWF_FIT_CONCURRENT") && atoi(getenv("NPSWF_FIT_CONCURRENT")) == 0);
         CR(cudaEventCreateWithFlags(&s.fit_fork, cudaEventDisableTiming));
         for (int i = 0; i < 2; i++) CR(cudaEventCreateWithFlags(&s.chunk_join[i], cudaEventDisableTiming));
@@ -814,11 +808,7 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
                     s.occ_front, s.occ_search, s.occ_fit_thread[1], s.occ_fit_thread[2], s.occ_fit_small[1], s.occ_fit_small[2],
                     s.occ_fit_small[3], s.occ_fit_big);
         if (s.occ_fit_thread[1] < 1 || s.occ_fit_thread[2] < 1 || s.occ_fit_thread[3] < 1) { h->err = "fit_thread_kernel does not fit on this device"; return fail(NPSWF_ERR_CUDA); }
-        s.fit2_group16 = getenv("NPSWF_FIT2_GROUP") && atoi(getenv("NPSWF_FIT2_GROUP")) == 16;
-        if (s.fit2_group16)
-            CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_small[2], fit_small_kernel<2, 16, 3>, FS_THREADS, 0));
-        else
-            CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_small[2], fit_small_kernel<2, 8, FS_MINB2>, FS_THREADS, 0));
+        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_small[2], fit_small_kernel<2, 8, FS_MINB2>, FS_THREADS, 0));
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_small[3], fit_small_kernel<3, 16, FS_MINB3>, FS_THREADS, 0));
         if (s.occ_front < 1 || s.occ_search < 1 || s.occ_fit_big < 1 || s.occ_fit_small[1] < 1 ||
             s.occ_fit_small[2] < 1 || s.occ_fit_small[3] < 1) {
