@@ -46,29 +46,28 @@ public:
     std::vector<EventResult> analyze(int64_t n_events, const double *signal, const int32_t *pres,
                                      const double *corr_time_HMS)
     {
-        const size_t nb = (size_t)n_events * NPSWF_NBLOCKS;
-        std::vector<int32_t> n(nb);
-        std::vector<double> t(nb * NPSWF_MAXWFPULSES), a(nb * NPSWF_MAXWFPULSES), c(nb), tw(nb), aw(nb);
-        std::vector<uint8_t> st(nb);
-        check(npswf_analyze_batch(h_, n_events, signal, pres, corr_time_HMS, n.data(), t.data(), a.data(), c.data(),
-                                  tw.data(), aw.data(), st.data()));
-        std::vector<EventResult> out((size_t)n_events);
-        for (int64_t e = 0; e < n_events; e++) {
-            EventResult &r = out[(size_t)e];
-            const size_t o = (size_t)e * NPSWF_NBLOCKS;
-            r.chi2.assign(c.begin() + o, c.begin() + o + NPSWF_NBLOCKS);
-            r.timewf.assign(tw.begin() + o, tw.begin() + o + NPSWF_NBLOCKS);
-            r.amplwf.assign(aw.begin() + o, aw.begin() + o + NPSWF_NBLOCKS);
-            r.wfnpulse.assign(n.begin() + o, n.begin() + o + NPSWF_NBLOCKS);
-            r.blockOffset.resize(NPSWF_NBLOCKS + 1);
-            r.wftime.resize((size_t)NPSWF_NBLOCKS * NPSWF_MAXWFPULSES);
-            r.wfampl.resize((size_t)NPSWF_NBLOCKS * NPSWF_MAXWFPULSES);
-            const int64_t tot = npswf_flatten_event(&n[o], &t[o * NPSWF_MAXWFPULSES], &a[o * NPSWF_MAXWFPULSES],
-                                                    r.wftime.data(), r.wfampl.data(), r.blockOffset.data());
-            r.wftime.resize((size_t)tot);
-            r.wfampl.resize((size_t)tot);
-        }
-        return out;
+        Padded p(n_events);
+        check(npswf_analyze_batch(h_, n_events, signal, pres, corr_time_HMS, p.n.data(), p.t.data(), p.a.data(), p.c.data(),
+                                  p.tw.data(), p.aw.data(), p.st.data()));
+        return flatten(n_events, p);
+    }
+
+    // The same, fed with what the reference's analyze receives (T2:540): the packed branch
+    // NPS.cal.fly.adcSampWaveform of the events, concatenated, event e = samp[offsets[e] .. offsets[e+1])
+    // (offsets = prefix sums of Ndata.NPS.cal.fly.adcSampWaveform).  The unpack of T2:851-889 runs on the device.
+    std::vector<EventResult> analyze_packed(int64_t n_events, const double *samp, const int64_t *offsets,
+                                            const double *corr_time_HMS)
+    {
+        Padded p(n_events);
+        check(npswf_analyze_batch_packed(h_, n_events, samp, offsets, corr_time_HMS, p.n.data(), p.t.data(), p.a.data(),
+                                         p.c.data(), p.tw.data(), p.aw.data(), p.st.data()));
+        return flatten(n_events, p);
+    }
+
+    // WF-tree diagnostics (T2:1026-1056): ampl[E][1080], enertot[E], integtot[E]
+    void diagnostics(int64_t n_events, const double *signal, double *ampl, double *enertot, double *integtot)
+    {
+        check(npswf_event_diagnostics_batch(h_, n_events, signal, ampl, enertot, integtot));
     }
 
     // Stage-level mirrors (batched): FindPulsesMF (T2:124), PassClusterThreshold (T2:218), Fitwf (T2:601)
@@ -95,6 +94,37 @@ public:
     npswf_handle *raw() { return h_; }
 
 private:
+    struct Padded {
+        std::vector<int32_t> n;
+        std::vector<double> t, a, c, tw, aw;
+        std::vector<uint8_t> st;
+        explicit Padded(int64_t E)
+            : n((size_t)E * NPSWF_NBLOCKS), t(n.size() * NPSWF_MAXWFPULSES), a(n.size() * NPSWF_MAXWFPULSES), c(n.size()),
+              tw(n.size()), aw(n.size()), st(n.size())
+        {
+        }
+    };
+    // padded [E][1080][12] arrays -> the reference's flattened per-event vectors (T2:1289-1296)
+    static std::vector<EventResult> flatten(int64_t n_events, const Padded &p)
+    {
+        std::vector<EventResult> out((size_t)n_events);
+        for (int64_t e = 0; e < n_events; e++) {
+            EventResult &r = out[(size_t)e];
+            const size_t o = (size_t)e * NPSWF_NBLOCKS;
+            r.chi2.assign(p.c.begin() + o, p.c.begin() + o + NPSWF_NBLOCKS);
+            r.timewf.assign(p.tw.begin() + o, p.tw.begin() + o + NPSWF_NBLOCKS);
+            r.amplwf.assign(p.aw.begin() + o, p.aw.begin() + o + NPSWF_NBLOCKS);
+            r.wfnpulse.assign(p.n.begin() + o, p.n.begin() + o + NPSWF_NBLOCKS);
+            r.blockOffset.resize(NPSWF_NBLOCKS + 1);
+            r.wftime.resize((size_t)NPSWF_NBLOCKS * NPSWF_MAXWFPULSES);
+            r.wfampl.resize((size_t)NPSWF_NBLOCKS * NPSWF_MAXWFPULSES);
+            const int64_t tot = npswf_flatten_event(&p.n[o], &p.t[o * NPSWF_MAXWFPULSES], &p.a[o * NPSWF_MAXWFPULSES],
+                                                    r.wftime.data(), r.wfampl.data(), r.blockOffset.data());
+            r.wftime.resize((size_t)tot);
+            r.wfampl.resize((size_t)tot);
+        }
+        return out;
+    }
     void check(int rc)
     {
         if (rc) throw std::runtime_error(std::string("npswf: ") + npswf_last_error(h_) + " (" + std::to_string(rc) + ")");

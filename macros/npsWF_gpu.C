@@ -1,7 +1,8 @@
 // npsWF_gpu.C — ROOT-side shim: how npsWF.C / TEST_2.C would call libnpswf.so.
 // NOT compiled or tested in this repo's environment (ROOT is not installed); kept deliberately small.
 // It replaces only T2:1305-1387 (Define("tuple", analyze) ... Snapshot): events are read in batches,
-// unpacked exactly as T2:851-889 does, analysed by ONE call per batch, and written to the WF tree
+// unpacked exactly as T2:851-889 does (or handed over packed: npswf::Analyzer::analyze_packed unpacks on the
+// device), analysed by ONE call per batch, and written to the WF tree
 // with the reference's branch names.  Everything before (chain, calibration loading T2:360-469) and
 // after (BuildIndex / CloneTree, T2:1395-1432) stays as in the reference.
 //

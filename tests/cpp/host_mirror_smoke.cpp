@@ -30,11 +30,26 @@ int main()
     if (npswf_device_count() > 0) { std::puts("gpu present: skipping the no-fallback check"); return 0; }
     std::vector<double> sig((size_t)B * T, 0.0), corr(1, 0.0);
     std::vector<int32_t> pres(B, 1);
+    int refused = 0;
     try {
         an.analyze(1, sig.data(), pres.data(), corr.data());
     } catch (const std::runtime_error &e) {
         std::printf("expected failure: %s\n", e.what());
-        return 0;
+        refused++;
     }
-    return 3;  // a CPU fallback would be a bug
+    std::vector<double> samp = {3, 110};
+    samp.resize(112, 1.0);
+    const int64_t offs[2] = {0, 112};
+    try {
+        an.analyze_packed(1, samp.data(), offs, corr.data());
+    } catch (const std::runtime_error &) {
+        refused++;
+    }
+    std::vector<double> ampl(B), et(1), it(1);
+    try {
+        an.diagnostics(1, sig.data(), ampl.data(), et.data(), it.data());
+    } catch (const std::runtime_error &) {
+        refused++;
+    }
+    return refused == 3 ? 0 : 3;  // a CPU fallback would be a bug
 }
