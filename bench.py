@@ -252,7 +252,8 @@ def main():
     # ---- end to end through npswf_analyze_batch: pinned host buffers, H2D + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
-        Ee = args.e2e_events
+        # per-rank pinned host buffers are ~1.4 MB per event: keep the node's total modest when many ranks share the host
+        Ee = args.e2e_events if world <= 2 else max(1184, args.e2e_events // (world // 2))
         hs = pkg.pinned_empty((Ee, NB, NT), np.float64)
         hp = pkg.pinned_empty((Ee, NB), np.int32)
         hc = pkg.pinned_empty((Ee,), np.float64)
