@@ -113,6 +113,21 @@ int npswf_analyze_batch_i16(npswf_handle *h, int64_t n_events, const int16_t *co
                             const int32_t *pres, const double *corr_time_HMS, int32_t *wfnpulse, double *wftime,
                             double *wfampl, double *chi2, double *timewf, double *amplwf, uint8_t *status);
 
+/* Transport of npswf_analyze_batch's binary64 traces.  The reference's samples are ADC counts * ADCtomV (1000/4096 mV,
+ * T2:357), so a chunk is sent to the device as int16 counts whenever that reproduces every double of the chunk bit for
+ * bit (checked sample by sample by `n_threads` host threads while the device works on the previous chunk); any other
+ * chunk goes over as the caller's doubles.  The kernels see identical traces either way, so results do not depend on
+ * the mode.  mode: 0 = always the doubles; 1 = automatic (default: packed while the host threads keep ahead of what
+ * the raw upload would do); 2 = packed whenever lossless.  n_threads = 0 and lsb_mV = 0 keep the current values
+ * (default: this process's share of the host cores, at most 16; 1000/4096).  Environment: NPSWF_HOST_PACK,
+ * NPSWF_HOST_PACK_THREADS set the defaults at npswf_create. */
+int npswf_set_host_packing(npswf_handle *h, int mode, int n_threads, double lsb_mV);
+/* Since npswf_create: chunks with a part sent as int16 counts / chunks whose packing was refused (sent as doubles) /
+ * mean packing rate (GB/s of doubles read) / bytes of the caller's doubles that travelled as counts (a quarter of it
+ * crossed PCIe).  Any pointer may be NULL. */
+int npswf_host_packing_stats(const npswf_handle *h, int64_t *packed_chunks, int64_t *raw_chunks, double *pack_gb_per_s,
+                             int64_t *packed_input_bytes);
+
 /* Same, all pointers DEVICE memory on the handle's device `dev_slot` (index into cfg.devices),
  * enqueued on `stream` (a cudaStream_t; NULL = the library's own stream) and NOT synchronised. */
 int npswf_analyze_batch_device(npswf_handle *h, int32_t dev_slot, int64_t n_events, const double *d_signal,

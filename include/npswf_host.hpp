@@ -91,6 +91,8 @@ public:
         check(npswf_get_counters(h_, &c));
         return c;
     }
+    // Transport of analyze()'s binary64 traces (npswf_set_host_packing): 0 doubles, 1 automatic, 2 counts whenever lossless.
+    void set_host_packing(int mode, int n_threads = 0, double lsb_mV = 0.0) { check(npswf_set_host_packing(h_, mode, n_threads, lsb_mV)); }
     npswf_handle *raw() { return h_; }
 
 private:

@@ -56,7 +56,7 @@ EXPORTS = [
     "npswf_tspectrum_debug", "npswf_get_mf_calib", "npswf_get_spline", "npswf_device_spline",
     "npswf_device_timeref", "npswf_flatten_event", "npswf_debug_exp", "npswf_debug_exact_ops", "npswf_debug_fp64_peak", "npswf_unpack_batch", "npswf_analyze_batch_packed",
     "npswf_event_diagnostics_batch", "npswf_event_diagnostics_device", "npswf_set_profiling",
-    "npswf_get_stage_times",
+    "npswf_get_stage_times", "npswf_set_host_packing", "npswf_host_packing_stats",
 ]
 
 _lib = None
@@ -221,6 +221,15 @@ class NpsWf:
 
     def reset_counters(self):
         self._check(lib().npswf_reset_counters(self.h))
+
+    def set_host_packing(self, mode=1, n_threads=0, lsb_mV=0.0):
+        """Transport of analyze()'s binary64 traces: 0 = doubles, 1 = automatic, 2 = int16 counts whenever lossless."""
+        self._check(lib().npswf_set_host_packing(self.h, C.c_int(mode), C.c_int(n_threads), C.c_double(lsb_mV)))
+
+    def host_packing_stats(self):
+        a, b, r, n = C.c_int64(), C.c_int64(), C.c_double(), C.c_int64()
+        self._check(lib().npswf_host_packing_stats(self.h, C.byref(a), C.byref(b), C.byref(r), C.byref(n)))
+        return dict(packed_chunks=a.value, raw_chunks=b.value, pack_gb_per_s=r.value, packed_input_bytes=n.value)
 
     # ---- analyze(event) over a batch (T2:540-1300 hot path)
     @staticmethod

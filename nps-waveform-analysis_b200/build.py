@@ -27,7 +27,7 @@ def build(force=False, verbose=False):
     os.makedirs(os.path.dirname(out), exist_ok=True)
     if force or _stale(out, srcs):
         cmd = [NVCC] + ARCH + COMMON + (["-Xptxas", "-v"] if verbose else []) + \
-              ["-o", out, os.path.join(csrc, "npswf_api.cu")]
+              ["-o", out, os.path.join(csrc, "npswf_api.cu"), os.path.join(csrc, "host_pack.cpp")]
         subprocess.check_call(cmd)
     syn = os.path.join(ROOT, "synth")
     sout = os.path.join(syn, "libnpswf_synth_cuda.so")

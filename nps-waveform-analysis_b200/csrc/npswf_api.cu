@@ -21,6 +21,9 @@
 #include "kernel_fit_small.cuh"
 #include "kernel_fit_thread.cuh"
 #include "kernel_aux.cuh"
+#include "host_pack.hpp"
+#include <chrono>
+#include <memory>
 
 using namespace npswf;
 
@@ -73,6 +76,15 @@ struct DevSlot {
     int occ_front = 2, occ_search = 4, occ_fit_big = 1, occ_fit_small[4] = {0, 4, 4, 2};  // resident CTAs per SM
     std::vector<cudaEvent_t> prof_events;  // 4 per profiled chunk: start, after front, after search, after fits
     std::vector<cudaEvent_t> prof_pool;
+    // lossless int16 transport of the binary64 host layout (host_pack.hpp): pool, three pinned staging buffers
+    std::unique_ptr<PackPool> packer;
+    int16_t *stage[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t stage_ev[3] = {nullptr, nullptr, nullptr};   // upload out of the staging buffer has completed
+    bool stage_busy[3] = {false, false, false};
+    size_t stage_cap = 0;                                    // samples per staging buffer
+    int64_t packed_chunks = 0, raw_chunks = 0;
+    double pack_seconds = 0, pack_bytes = 0;
+    double pack_rate = 0;                                    // running estimate, bytes of doubles per second
 };
 
 }  // namespace
@@ -88,6 +100,9 @@ struct npswf_handle {
     int64_t chunk = 1184;  // events per chunk (8 x 148 SMs): large enough to amortise the fit kernels' tails
     std::mutex mu;
     bool profiling = false;
+    int pack_mode = 1;                 // 0 off, 1 auto (on while it is faster than the raw upload), 2 always
+    int pack_threads = 0;              // host threads per device
+    double pack_lsb = 1000.0 / 4096;   // ADCtomV, T2:357
     double stage_ms[3] = {0, 0, 0};  // front, search, fit
     int64_t stage_chunks = 0;
 };
@@ -485,15 +500,82 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
     if (hi - lo > 2 * 296)
         chunk = std::min<int64_t>(h->chunk, std::max<int64_t>(296, ((hi - lo + target * 148 - 1) / (target * 148)) * 148));
     cudaStream_t s_in = s.copy_in, s_out = s.copy_out, s_cmp = s.ws[0].stream;
+    // binary64 host layout: events go over as int16 counts when that is lossless (host_pack.hpp).  The host threads
+    // (pack_rate, measured) and the copy engine (~48 GB/s from pinned memory) feed the device side by side: in auto
+    // mode the first n_raw events of every chunk are uploaded as they are while the host packs the rest, with the
+    // split chosen so that both finish together -- (1-f) / pack_rate = (f + (1-f)/4) / dma_rate.  From pageable memory
+    // the raw upload is slow and blocks the caller, so everything is packed.
+    const bool pack = io.signal && !io.counts && !io.packed && h->pack_mode != 0;
+    bool pinned_src = false;
+    if (pack) {
+        if (!s.packer) s.packer.reset(new PackPool(h->pack_threads));
+        const size_t need = (size_t)std::min<int64_t>(chunk, hi - lo) * B * T;
+        if (need > s.stage_cap) {
+            for (int i = 0; i < 3; i++) {
+                if (s.stage_busy[i]) CU_TRY(h, cudaEventSynchronize(s.stage_ev[i]));
+                s.stage_busy[i] = false;
+                if (s.stage[i]) CU_TRY(h, cudaFreeHost(s.stage[i]));
+                s.stage[i] = nullptr;
+                CU_TRY(h, cudaHostAlloc((void **)&s.stage[i], need * sizeof(int16_t), cudaHostAllocPortable));
+                if (!s.stage_ev[i]) CU_TRY(h, cudaEventCreateWithFlags(&s.stage_ev[i], cudaEventDisableTiming));
+            }
+            s.stage_cap = need;
+        }
+        cudaPointerAttributes at{};
+        pinned_src = cudaPointerGetAttributes(&at, io.signal) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        (void)cudaGetLastError();
+        if (s.pack_rate <= 0) s.pack_rate = 4.0e9 * s.packer->threads();
+    }
     int which = 0;
     int64_t k = 0;
     for (int64_t e0 = lo; e0 < hi; e0 += chunk, which ^= 1, k++) {
         Workspace &w = s.ws[which];
         const int64_t n = std::min<int64_t>(chunk, hi - e0);
         const size_t nb = (size_t)n * B, ob = (size_t)e0 * B;
+        // events [0, n_raw) of the chunk travel as doubles, [n_raw, n) as counts
+        int64_t n_raw = n;
+        if (pack) {
+            double f = 0.0;
+            if (h->pack_mode == 1 && pinned_src) {
+                const double a = 48.0e9 / s.pack_rate;
+                f = std::min(1.0, std::max(0.0, (a - 0.25) / (a + 0.75)));
+                if (f > 0.9) f = 1.0;
+            }
+            n_raw = std::min<int64_t>(n, (int64_t)(f * (double)n + 0.5));
+        }
+        const int64_t n_cnt = n - n_raw;
+        bool staged = false;
         // upload: the workspace must have been drained by the download of chunk k - 2
         if (k >= 2) CU_TRY(h, cudaStreamWaitEvent(s_in, w.ev_out, 0));
-        if (io.packed) {
+        if (pack) {
+            // the raw part first: the copy engine works on it while the host packs the rest
+            if (n_raw > 0)
+                CU_TRY(h, cudaMemcpyAsync(w.signal, io.signal + ob * T, (size_t)n_raw * B * T * sizeof(double), cudaMemcpyHostToDevice, s_in));
+            if (n_cnt > 0) {
+                const int sb = (int)(k % 3);
+                const size_t off = (size_t)n_raw * B * T, cnt = (size_t)n_cnt * B * T;
+                if (s.stage_busy[sb]) CU_TRY(h, cudaEventSynchronize(s.stage_ev[sb]));
+                s.stage_busy[sb] = false;
+                const auto t0 = std::chrono::steady_clock::now();
+                staged = s.packer->pack(io.signal + ob * T + off, s.stage[sb], cnt, h->pack_lsb);
+                const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                if (staged) {
+                    s.packed_chunks++;
+                    s.pack_seconds += dt;
+                    s.pack_bytes += (double)cnt * sizeof(double);
+                    if (dt > 0) s.pack_rate = 0.5 * s.pack_rate + 0.5 * (double)cnt * sizeof(double) / dt;
+                    if (!w.counts) {
+                        if ((rc = dev_alloc(h, s, &w.counts, (size_t)w.cap * B * T))) return rc;
+                    }
+                    CU_TRY(h, cudaMemcpyAsync(w.counts, s.stage[sb], cnt * sizeof(int16_t), cudaMemcpyHostToDevice, s_in));
+                    CU_TRY(h, cudaEventRecord(s.stage_ev[sb], s_in));
+                    s.stage_busy[sb] = true;
+                } else {   // not on the lattice: the caller's doubles
+                    s.raw_chunks++;
+                    CU_TRY(h, cudaMemcpyAsync(w.signal + off, io.signal + ob * T + off, cnt * sizeof(double), cudaMemcpyHostToDevice, s_in));
+                }
+            }
+        } else if (io.packed) {
             const size_t words = (size_t)(io.offsets[e0 + n] - io.offsets[e0]);
             if (!w.poffs) {
                 if ((rc = dev_alloc(h, s, &w.poffs, (size_t)w.cap + 1))) return rc;
@@ -522,6 +604,11 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
         if (io.packed) {
             unpack_kernel<<<(unsigned)std::min<int64_t>(n, 4 * s.sm_count), UNPACK_THREADS, 0, s_cmp>>>(
                 w.packed, w.poffs, (long long)io.offsets[e0], n, w.signal, w.pres);
+            CU_TRY(h, cudaGetLastError());
+        } else if (staged) {
+            const long long tot = (long long)n_cnt * B * T;
+            widen_counts_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s_cmp>>>(w.counts, w.signal + (size_t)n_raw * B * T,
+                                                                                  h->pack_lsb, tot);
             CU_TRY(h, cudaGetLastError());
         } else if (io.counts) {
             const long long tot = (long long)nb * T;
@@ -614,6 +701,16 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
     h->kp.fit_retry_max_iter = cfg->fit_retry_max_iter > 0 ? cfg->fit_retry_max_iter : 100;
     h->kp.fit_thread_tries = (getenv("NPSWF_FIT_THREAD_TRIES") && atoi(getenv("NPSWF_FIT_THREAD_TRIES")) > 0) ? atoi(getenv("NPSWF_FIT_THREAD_TRIES")) : 20;
     h->chunk = cfg->chunk_events > 0 ? cfg->chunk_events : 1184;
+    {
+        // host threads for the lossless int16 transport: the cores of this process's share of the node, at most 16
+        const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+        const int local = (getenv("LOCAL_WORLD_SIZE") && atoi(getenv("LOCAL_WORLD_SIZE")) > 0) ? atoi(getenv("LOCAL_WORLD_SIZE")) : 1;
+        const int nd = std::max(1, cfg->n_devices);
+        h->pack_threads = std::min(16, std::max(1, hw / (local * nd)));
+        if (getenv("NPSWF_HOST_PACK_THREADS") && atoi(getenv("NPSWF_HOST_PACK_THREADS")) > 0)
+            h->pack_threads = atoi(getenv("NPSWF_HOST_PACK_THREADS"));
+        if (getenv("NPSWF_HOST_PACK")) h->pack_mode = std::min(2, std::max(0, atoi(getenv("NPSWF_HOST_PACK"))));
+    }
     // ---- derived calibration on the host (T2:440-451 for mfyref/mfint; spline coefficients)
     h->mfyref.assign((size_t)B * MFW, 0.0);
     h->mfint.assign(B, 0.0);
@@ -847,8 +944,38 @@ void npswf_destroy(npswf_handle *h)
         for (cudaEvent_t e : s.prof_events) cudaEventDestroy(e);
         for (cudaEvent_t e : s.prof_pool) cudaEventDestroy(e);
         for (void *p : s.owned) cudaFree(p);
+        for (int i = 0; i < 3; i++) {
+            if (s.stage[i]) cudaFreeHost(s.stage[i]);
+            if (s.stage_ev[i]) cudaEventDestroy(s.stage_ev[i]);
+        }
     }
     delete h;
+}
+
+int npswf_set_host_packing(npswf_handle *h, int mode, int n_threads, double lsb_mV)
+{
+    if (!h || mode < 0 || mode > 2 || n_threads < 0 || !(lsb_mV >= 0)) return NPSWF_ERR_ARG;
+    h->pack_mode = mode;
+    if (lsb_mV > 0) h->pack_lsb = lsb_mV;
+    if (n_threads > 0 && n_threads != h->pack_threads) {
+        h->pack_threads = n_threads;
+        for (DevSlot &s : h->slots) s.packer.reset();
+    }
+    return 0;
+}
+
+int npswf_host_packing_stats(const npswf_handle *h, int64_t *packed_chunks, int64_t *raw_chunks, double *pack_gb_per_s,
+                             int64_t *packed_input_bytes)
+{
+    if (!h) return NPSWF_ERR_ARG;
+    int64_t p = 0, r = 0;
+    double sec = 0, bytes = 0;
+    for (const DevSlot &s : h->slots) { p += s.packed_chunks; r += s.raw_chunks; sec += s.pack_seconds; bytes += s.pack_bytes; }
+    if (packed_chunks) *packed_chunks = p;
+    if (raw_chunks) *raw_chunks = r;
+    if (pack_gb_per_s) *pack_gb_per_s = sec > 0 ? bytes / sec / 1e9 : 0.0;
+    if (packed_input_bytes) *packed_input_bytes = (int64_t)bytes;
+    return 0;
 }
 
 int npswf_get_counters(npswf_handle *h, NpsWfCounters *out)

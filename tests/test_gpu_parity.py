@@ -457,3 +457,43 @@ def test_two_devices_in_one_process_equal_one_device(pkg, calib, spline):
         assert np.array_equal(one[k], two[k]), k
     c = h2.counters()
     assert c["n_events"] == E and c["n_fit_attempted"] == int(((one["status"] & 28) > 0).sum())
+
+
+def test_host_packing_is_lossless_and_falls_back(pkg, calib, events):
+    """npswf_analyze_batch sends lattice chunks as int16 counts (host_pack.hpp) and everything else as the caller's
+    doubles; outputs are bit-identical in every mode."""
+    ev = events[2]
+    sig, pres, corr = ev["signal"], ev["pres"], ev["corr_time_HMS"]
+    h = pkg.NpsWf(calib)
+    h.set_host_packing(0)
+    raw = h.analyze(sig, pres, corr)
+    assert h.host_packing_stats()["packed_chunks"] == 0
+    h.set_host_packing(2, n_threads=3)
+    packed = h.analyze(sig, pres, corr)
+    st = h.host_packing_stats()
+    assert st["packed_chunks"] >= 1 and st["raw_chunks"] == 0
+    for k in raw:
+        assert np.array_equal(raw[k], packed[k]), k
+    assert (np.signbit(sig) & (sig == 0)).any()   # the sets hold -0.0 samples: they travel as +0.0, no output differs
+    # one sample off the lattice / beyond int16 / tiny: the chunk goes over as doubles
+    for bad in (0.1, 40000 * 1000.0 / 4096, 2.0 ** -30):
+        s2 = sig.copy()
+        s2[1, 500, 57] = bad
+        h.set_host_packing(0)
+        a = h.analyze(s2, pres, corr)
+        before = h.host_packing_stats()
+        h.set_host_packing(2)
+        b = h.analyze(s2, pres, corr)
+        after = h.host_packing_stats()
+        assert after["raw_chunks"] == before["raw_chunks"] + 1 and after["packed_chunks"] == before["packed_chunks"], bad
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (bad, k)
+    # another lattice: counts * 0.5 mV
+    h.set_host_packing(2, lsb_mV=0.5)
+    s3 = np.round(sig * 2.0) / 2.0
+    c = h.analyze(s3, pres, corr)
+    assert h.host_packing_stats()["packed_chunks"] == after["packed_chunks"] + 1
+    h.set_host_packing(0)
+    d = h.analyze(s3, pres, corr)
+    for k in c:
+        assert np.array_equal(c[k], d[k]), k
