@@ -400,7 +400,7 @@ def main():
         import oracle
         orc = oracle.Oracle(cal)
         threads = os.cpu_count() or 1
-        probe = 2
+        probe = max(2, threads)   # one event per thread: the probe sees the parallel rate
         cap = min(1184, E)
         sig = bufs[0][0][:cap].cpu().numpy(); prs = bufs[0][1][:cap].cpu().numpy(); cor = bufs[0][2][:cap].cpu().numpy()
         t0 = time.perf_counter()
