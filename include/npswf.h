@@ -122,6 +122,10 @@ int npswf_analyze_batch_i16(npswf_handle *h, int64_t n_events, const int16_t *co
  * (default: this process's share of the host cores, at most 16; 1000/4096).  Environment: NPSWF_HOST_PACK,
  * NPSWF_HOST_PACK_THREADS set the defaults at npswf_create. */
 int npswf_set_host_packing(npswf_handle *h, int mode, int n_threads, double lsb_mV);
+/* Host-only tap of the packer (no device needed): counts_out[i] = round(x[i] / lsb_mV) with n_threads host threads;
+ * returns 1 if every x[i] == double(counts_out[i]) * lsb_mV with |counts| <= 32767 (the chunk would travel as counts),
+ * 0 if not (it would travel as doubles), < 0 on bad arguments. */
+int npswf_debug_pack_counts(const double *x, int64_t n, double lsb_mV, int32_t n_threads, int16_t *counts_out);
 /* Since npswf_create: chunks with a part sent as int16 counts / chunks whose packing was refused (sent as doubles) /
  * mean packing rate (GB/s of doubles read) / bytes of the caller's doubles that travelled as counts (a quarter of it
  * crossed PCIe).  Any pointer may be NULL. */

@@ -56,7 +56,7 @@ EXPORTS = [
     "npswf_tspectrum_debug", "npswf_get_mf_calib", "npswf_get_spline", "npswf_device_spline",
     "npswf_device_timeref", "npswf_flatten_event", "npswf_debug_exp", "npswf_debug_exact_ops", "npswf_debug_fp64_peak", "npswf_unpack_batch", "npswf_analyze_batch_packed",
     "npswf_event_diagnostics_batch", "npswf_event_diagnostics_device", "npswf_set_profiling",
-    "npswf_get_stage_times", "npswf_set_host_packing", "npswf_host_packing_stats",
+    "npswf_get_stage_times", "npswf_set_host_packing", "npswf_host_packing_stats", "npswf_debug_pack_counts",
 ]
 
 _lib = None
@@ -93,6 +93,17 @@ def _p(a):
 
 def _c(a, dtype):
     return np.ascontiguousarray(a, dtype=dtype)
+
+
+def pack_counts(x, lsb_mV=1000.0 / 4096, n_threads=2):
+    """Host-only tap of the lossless int16 transport packer: returns (lossless, counts)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty(x.shape, dtype=np.int16)
+    rc = lib().npswf_debug_pack_counts(x.ctypes.data_as(C.c_void_p), C.c_int64(x.size), C.c_double(lsb_mV),
+                                       C.c_int32(n_threads), out.ctypes.data_as(C.c_void_p))
+    if rc < 0:
+        raise NpsWfError(rc, "npswf_debug_pack_counts: bad arguments")
+    return bool(rc), out
 
 
 def pinned_empty(shape, dtype):

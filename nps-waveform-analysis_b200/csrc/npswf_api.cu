@@ -964,6 +964,13 @@ int npswf_set_host_packing(npswf_handle *h, int mode, int n_threads, double lsb_
     return 0;
 }
 
+int npswf_debug_pack_counts(const double *x, int64_t n, double lsb_mV, int32_t n_threads, int16_t *counts_out)
+{
+    if (!x || !counts_out || n < 0 || !(lsb_mV > 0) || n_threads < 1) return NPSWF_ERR_ARG;
+    PackPool pool(n_threads);
+    return pool.pack(x, counts_out, (size_t)n, lsb_mV) ? 1 : 0;
+}
+
 int npswf_host_packing_stats(const npswf_handle *h, int64_t *packed_chunks, int64_t *raw_chunks, double *pack_gb_per_s,
                              int64_t *packed_input_bytes)
 {

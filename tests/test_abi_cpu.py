@@ -100,3 +100,30 @@ def test_cpp_host_mirror_compiles_and_refuses_cpu(tmp_path, pkg):
                            "-L", libdir, "-lnpswf", "-Wl,-rpath," + libdir])
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_host_packer_accepts_exactly_the_lattice(pkg, calib, spline):
+    """The lossless int16 transport (csrc/host_pack.*): a chunk is packed iff every double is count * lsb."""
+    import synth
+    ev = synth.generate_host(synth.config_params(2), spline, calib, 77, 2, n_threads=2, counts=True)
+    sig = ev["signal"]
+    for nt in (1, 3, 8):
+        ok, k = pkg.pack_counts(sig, synth.LSB, n_threads=nt)
+        assert ok and np.array_equal(k, ev["counts"])
+        assert np.array_equal(k.astype(np.float64) * synth.LSB, sig)      # what the device computes from the counts
+    lsb = synth.LSB
+    edge = np.array([32767 * lsb, -32767 * lsb, 0.0, -0.0, lsb, -lsb] * 3)   # odd length: vector body + scalar tail
+    ok, k = pkg.pack_counts(edge, lsb)
+    assert ok and k[0] == 32767 and k[1] == -32767 and k[2] == 0 and k[3] == 0
+    for bad in (0.1, 32768 * lsb, -32768 * lsb, np.nan, np.inf, -np.inf, 2.0 ** -40, lsb * (1 + 2.0 ** -52), 1e300):
+        for pos in (0, 5, len(edge) - 1):
+            x = edge.copy()
+            x[pos] = bad
+            assert not pkg.pack_counts(x, lsb)[0], (bad, pos)
+    big = np.tile(sig.reshape(-1), 3)
+    big[big.size // 2 + 12345] += 2.0 ** -20
+    assert not pkg.pack_counts(big, lsb, n_threads=4)[0]
+    # other lattices
+    assert pkg.pack_counts(np.arange(-50, 50) * 0.5, 0.5)[0]
+    assert not pkg.pack_counts(np.arange(-50, 50) * 0.25, 0.5)[0]
+    assert pkg.pack_counts(np.zeros(0), lsb)[0]
