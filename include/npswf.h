@@ -107,6 +107,19 @@ int npswf_analyze_batch(npswf_handle *h, int64_t n_events, const double *signal,
                         const double *corr_time_HMS, int32_t *wfnpulse, double *wftime, double *wfampl,
                         double *chi2, double *timewf, double *amplwf, uint8_t *status);
 
+/* Same analysis, with wfampl / wftime in the reference's own output packing (T2:959-961, 1289-1296): the vectors of
+ * event e -- the pulses of its blocks in block order, sum of wfnpulse of them -- are
+ *   wftime_pool[pulse_offset[e] .. + pulse_count[e]),  wfampl_pool[same range].
+ * Packed on the device, so only the pulses cross PCIe (a few % of the padded [1080][12] arrays) and the caller has no
+ * flatten pass.  pool_capacity = doubles available in each pool; with n devices, device d's event range uses the
+ * d-th share of the pools (offsets are absolute; ranges of different devices need not touch).  A pool that is too
+ * small -> NPSWF_ERR_NOMEM (npswf_last_error says how much was missing); E * 12960 always suffices.
+ * wfnpulse, chi2, timewf, amplwf, status: as npswf_analyze_batch (may be NULL); n_pulses (may be NULL): total. */
+int npswf_analyze_batch_flat(npswf_handle *h, int64_t n_events, const double *signal, const int32_t *pres,
+                             const double *corr_time_HMS, int32_t *wfnpulse, int64_t *pulse_offset, int32_t *pulse_count,
+                             double *wftime_pool, double *wfampl_pool, int64_t pool_capacity, double *chi2, double *timewf,
+                             double *amplwf, uint8_t *status, int64_t *n_pulses);
+
 /* Same, with inputs as int16 ADC counts (signal = counts * lsb_mV; exact on the 12-bit lattice
  * 1000/4096 mV of T2:357).  Quarter of the PCIe bytes. */
 int npswf_analyze_batch_i16(npswf_handle *h, int64_t n_events, const int16_t *counts, double lsb_mV,

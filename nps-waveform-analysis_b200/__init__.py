@@ -56,7 +56,7 @@ EXPORTS = [
     "npswf_tspectrum_debug", "npswf_get_mf_calib", "npswf_get_spline", "npswf_device_spline",
     "npswf_device_timeref", "npswf_flatten_event", "npswf_debug_exp", "npswf_debug_exact_ops", "npswf_debug_fp64_peak", "npswf_unpack_batch", "npswf_analyze_batch_packed",
     "npswf_event_diagnostics_batch", "npswf_event_diagnostics_device", "npswf_set_profiling",
-    "npswf_get_stage_times", "npswf_set_host_packing", "npswf_host_packing_stats", "npswf_debug_pack_counts",
+    "npswf_get_stage_times", "npswf_set_host_packing", "npswf_host_packing_stats", "npswf_debug_pack_counts", "npswf_analyze_batch_flat",
 ]
 
 _lib = None
@@ -261,6 +261,31 @@ class NpsWf:
                                               _p(o["wftime"]), _p(o["wfampl"]), _p(o["chi2"]), _p(o["timewf"]),
                                               _p(o["amplwf"]), _p(o["status"])))
         return o
+
+    @staticmethod
+    def alloc_flat_outputs(E, capacity, pinned=False):
+        mk = pinned_empty if pinned else (lambda s, d: np.empty(s, d))
+        return dict(wfnpulse=mk((E, NBLOCKS), np.int32), pulse_offset=mk((E,), np.int64), pulse_count=mk((E,), np.int32),
+                    wftime_pool=mk((capacity,), np.float64), wfampl_pool=mk((capacity,), np.float64),
+                    chi2=mk((E, NBLOCKS), np.float64), timewf=mk((E, NBLOCKS), np.float64),
+                    amplwf=mk((E, NBLOCKS), np.float64), status=mk((E, NBLOCKS), np.uint8))
+
+    def analyze_flat(self, signal, pres, corr_time_HMS, capacity=None, out=None):
+        """analyze() with wfampl / wftime in the reference's own packing (T2:1289-1296): event e's vectors are
+        pool[pulse_offset[e] : pulse_offset[e] + pulse_count[e]], pulses in block order.  Packed on the device."""
+        sig = _c(signal, np.float64).reshape(-1, NBLOCKS, NTIME)
+        E = sig.shape[0]
+        pr = _c(pres, np.int32).reshape(E, NBLOCKS)
+        co = _c(corr_time_HMS, np.float64).reshape(E)
+        if out is None:
+            out = self.alloc_flat_outputs(E, capacity if capacity is not None else E * NBLOCKS * MAXWFPULSES)
+        npul = C.c_int64(0)
+        self._check(lib().npswf_analyze_batch_flat(
+            self.h, C.c_int64(E), _p(sig), _p(pr), _p(co), _p(out["wfnpulse"]), _p(out["pulse_offset"]), _p(out["pulse_count"]),
+            _p(out["wftime_pool"]), _p(out["wfampl_pool"]), C.c_int64(out["wftime_pool"].size), _p(out["chi2"]),
+            _p(out["timewf"]), _p(out["amplwf"]), _p(out["status"]), C.byref(npul)))
+        out["n_pulses"] = npul.value
+        return out
 
     def analyze_i16(self, counts, lsb_mV, pres, corr_time_HMS, out=None):
         cn = _c(counts, np.int16).reshape(-1, NBLOCKS, NTIME)

@@ -140,4 +140,103 @@ diag_kernel(const double *__restrict__ signal, long long n_events, double *__res
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Output packing (T2:959-961, 1022, 1289-1296): the reference returns wfampl / wftime as vectors truncated to
+// blockOffset[1080] = sum of wfnpulse -- the pulses of the blocks in block order.  Done on the device so that only
+// the pulses cross PCIe instead of the padded [1080][12] arrays (of which ~1.5 of 12 slots are used).
+//   flat_totals_kernel : pulses per event
+//   flat_scan_kernel   : exclusive scan over the events of the chunk (one CTA; n_events <= a few thousand)
+//   flat_scatter_kernel: per event, exclusive scan over the blocks (= blockOffset) and the copy
+constexpr int FLAT_THREADS = 256;
+
+__device__ __forceinline__ int clamp_npulse(int n) { return n < 0 ? 0 : (n > MAXP ? MAXP : n); }
+
+__global__ void __launch_bounds__(FLAT_THREADS)
+flat_totals_kernel(const int32_t *__restrict__ wfnpulse, long long n_events, int *__restrict__ ev_total)
+{
+    __shared__ int wsum[FLAT_THREADS / 32];
+    for (long long e = blockIdx.x; e < n_events; e += gridDim.x) {
+        int v = 0;
+        for (int b = threadIdx.x; b < B; b += FLAT_THREADS) v += clamp_npulse(wfnpulse[(size_t)e * B + b]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < FLAT_THREADS / 32; w++) t += wsum[w];
+            ev_total[e] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// ev_off[0 .. n_events]: exclusive prefix sums of ev_total (int: a chunk holds at most cap * 12 960 pulses)
+__global__ void __launch_bounds__(1024) flat_scan_kernel(const int *__restrict__ ev_total, long long n_events, int *__restrict__ ev_off)
+{
+    __shared__ int part[1024];
+    const int t = threadIdx.x;
+    const long long per = (n_events + 1023) / 1024;
+    const long long lo = (long long)t * per, hi = (lo + per < n_events) ? lo + per : n_events;
+    int s = 0;
+    for (long long i = lo; i < hi; i++) s += ev_total[i];
+    part[t] = s;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over the 1024 partial sums
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = (t >= o) ? part[t - o] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    int run = (t == 0) ? 0 : part[t - 1];
+    for (long long i = lo; i < hi; i++) {
+        ev_off[i] = run;
+        run += ev_total[i];
+    }
+    if (t == 1023) ev_off[n_events] = part[1023];
+}
+
+__global__ void __launch_bounds__(FLAT_THREADS)
+flat_scatter_kernel(const int32_t *__restrict__ wfnpulse, const double *__restrict__ wftime, const double *__restrict__ wfampl,
+                    long long n_events, const int *__restrict__ ev_off, double *__restrict__ flat_t, double *__restrict__ flat_a,
+                    int32_t *__restrict__ block_offset /* [E][1081] or null: the reference's blockOffset, T2:959, 1022 */)
+{
+    __shared__ int wsum[FLAT_THREADS / 32];
+    __shared__ int carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long e = blockIdx.x; e < n_events; e += gridDim.x) {
+        if (threadIdx.x == 0) carry = 0;
+        __syncthreads();
+        const size_t base = (size_t)ev_off[e];
+        for (int b0 = 0; b0 < B; b0 += FLAT_THREADS) {
+            const int b = b0 + threadIdx.x;
+            const int n = (b < B) ? clamp_npulse(wfnpulse[(size_t)e * B + b]) : 0;
+            int inc = n;   // inclusive scan within the warp
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            if (lane == 31) wsum[warp] = inc;
+            __syncthreads();
+            int before = carry;
+            for (int w = 0; w < warp; w++) before += wsum[w];
+            const int off = before + inc - n;
+            if (b < B) {
+                if (block_offset) block_offset[(size_t)e * (B + 1) + b] = off;
+                for (int p = 0; p < n; p++) {
+                    flat_t[base + off + p] = wftime[((size_t)e * B + b) * MAXP + p];
+                    flat_a[base + off + p] = wfampl[((size_t)e * B + b) * MAXP + p];
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == FLAT_THREADS - 1) carry = off + n;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0 && block_offset) block_offset[(size_t)e * (B + 1) + B] = carry;
+        __syncthreads();
+    }
+}
+
 }  // namespace npswf

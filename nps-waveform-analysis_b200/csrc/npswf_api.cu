@@ -55,6 +55,11 @@ struct Workspace {  // per (device, pipeline stage) buffers for up to `cap` even
     int *fit_dense = nullptr;     // [13][cap*B] block-major dense job lists (what the fit kernels read)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_cmp = nullptr, ev_out = nullptr;  // host-path pipeline: uploaded / computed / downloaded
+    // flat (reference-layout) outputs: pulses per event, their prefix sums, the packed pulses; host copy of the sums
+    int *ev_total = nullptr, *ev_off = nullptr;
+    double *flat_t = nullptr, *flat_a = nullptr;
+    int *h_ev_off = nullptr;          // pinned, [cap + 1]
+    cudaEvent_t ev_tot = nullptr;     // h_ev_off has arrived
     bool io = false;  // has the signal/pres/output staging buffers (host-buffer API) or only scratch
 };
 
@@ -480,6 +485,13 @@ struct HostIO {
     int32_t *wfnpulse = nullptr;
     double *wftime = nullptr, *wfampl = nullptr, *chi2 = nullptr, *timewf = nullptr, *amplwf = nullptr;
     uint8_t *status = nullptr;
+    // flat outputs (npswf_analyze_batch_flat)
+    bool flat = false;
+    int64_t *pulse_offset = nullptr;
+    int32_t *pulse_count = nullptr;
+    double *pool_t = nullptr, *pool_a = nullptr;
+    int64_t pool_cap = 0, n_total = 0;
+    int64_t *pulses_out = nullptr;   // [n_devices]: pulses written by each device range
 };
 
 // Chunked, double-buffered host pipeline on one device for events [lo, hi).
@@ -526,6 +538,51 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
         (void)cudaGetLastError();
         if (s.pack_rate <= 0) s.pack_rate = 4.0e9 * s.packer->threads();
     }
+    // flat outputs: this range owns the slice [pool_lo, pool_hi) of the caller's pulse pools; the copy of a chunk's
+    // pulses is enqueued one iteration later, when its pulse count has reached the host (no bubble in the pipeline)
+    int64_t pool_cur = 0, pool_hi = 0;
+    struct Pending { Workspace *w; int64_t e0, n; } pend{nullptr, 0, 0};
+    if (io.flat) {
+        pool_cur = (int64_t)((__int128)io.pool_cap * lo / io.n_total);
+        pool_hi = (int64_t)((__int128)io.pool_cap * hi / io.n_total);
+        for (int i = 0; i < 2; i++) {
+            Workspace &w = s.ws[i];
+            if (w.flat_t) continue;
+            if ((rc = dev_alloc(h, s, &w.ev_total, (size_t)w.cap))) return rc;
+            if ((rc = dev_alloc(h, s, &w.ev_off, (size_t)w.cap + 1))) return rc;
+            if ((rc = dev_alloc(h, s, &w.flat_t, (size_t)w.cap * B * MAXP))) return rc;
+            if ((rc = dev_alloc(h, s, &w.flat_a, (size_t)w.cap * B * MAXP))) return rc;
+            CU_TRY(h, cudaHostAlloc((void **)&w.h_ev_off, ((size_t)w.cap + 1) * sizeof(int), cudaHostAllocPortable));
+            CU_TRY(h, cudaEventCreateWithFlags(&w.ev_tot, cudaEventDisableTiming));
+        }
+    }
+    auto finish_flat = [&]() -> int {
+        if (!pend.w) return 0;
+        Workspace &pw = *pend.w;
+        CU_TRY(h, cudaEventSynchronize(pw.ev_tot));
+        const int64_t total = pw.h_ev_off[pend.n];
+        if (pool_cur + total > pool_hi) {
+            char b[256];
+            snprintf(b, sizeof b, "npswf_analyze_batch_flat: pulse pool too small (events %lld..%lld need %lld more pulses, %lld left in "
+                     "this range's share)", (long long)pend.e0, (long long)(pend.e0 + pend.n), (long long)total, (long long)(pool_hi - pool_cur));
+            h->err = b;
+            cudaDeviceSynchronize();   // leave nothing in flight that still reads or writes the caller's buffers
+            pend.w = nullptr;
+            return NPSWF_ERR_NOMEM;
+        }
+        if (total > 0) {
+            CU_TRY(h, cudaMemcpyAsync(io.pool_t + pool_cur, pw.flat_t, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+            CU_TRY(h, cudaMemcpyAsync(io.pool_a + pool_cur, pw.flat_a, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+        }
+        for (int64_t i = 0; i < pend.n; i++) {
+            if (io.pulse_offset) io.pulse_offset[pend.e0 + i] = pool_cur + pw.h_ev_off[i];
+            if (io.pulse_count) io.pulse_count[pend.e0 + i] = pw.h_ev_off[i + 1] - pw.h_ev_off[i];
+        }
+        pool_cur += total;
+        CU_TRY(h, cudaEventRecord(pw.ev_out, s_out));
+        pend.w = nullptr;
+        return 0;
+    };
     int which = 0;
     int64_t k = 0;
     for (int64_t e0 = lo; e0 < hi; e0 += chunk, which ^= 1, k++) {
@@ -618,7 +675,16 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
         rc = run_chunk(h, s, w, s_cmp, n, w.signal, w.pres, w.corr, w.wfnpulse, w.wftime, w.wfampl, w.chi2, w.timewf,
                        w.amplwf, w.status);
         if (rc) return rc;
+        if (io.flat) {
+            const unsigned g = (unsigned)std::min<int64_t>(n, 8 * s.sm_count);
+            flat_totals_kernel<<<g, FLAT_THREADS, 0, s_cmp>>>(w.wfnpulse, n, w.ev_total);
+            flat_scan_kernel<<<1, 1024, 0, s_cmp>>>(w.ev_total, n, w.ev_off);
+            flat_scatter_kernel<<<g, FLAT_THREADS, 0, s_cmp>>>(w.wfnpulse, w.wftime, w.wfampl, n, w.ev_off, w.flat_t, w.flat_a, nullptr);
+            CU_TRY(h, cudaGetLastError());
+        }
         CU_TRY(h, cudaEventRecord(w.ev_cmp, s_cmp));
+        // the pulses of the previous chunk go first on the download stream (its workspace is the next to be refilled)
+        if ((rc = finish_flat())) return rc;
         // download
         CU_TRY(h, cudaStreamWaitEvent(s_out, w.ev_cmp, 0));
         if (io.wfnpulse) CU_TRY(h, cudaMemcpyAsync(io.wfnpulse + ob, w.wfnpulse, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s_out));
@@ -628,8 +694,16 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
         if (io.timewf) CU_TRY(h, cudaMemcpyAsync(io.timewf + ob, w.timewf, nb * sizeof(double), cudaMemcpyDeviceToHost, s_out));
         if (io.amplwf) CU_TRY(h, cudaMemcpyAsync(io.amplwf + ob, w.amplwf, nb * sizeof(double), cudaMemcpyDeviceToHost, s_out));
         if (io.status) CU_TRY(h, cudaMemcpyAsync(io.status + ob, w.status, nb * sizeof(uint8_t), cudaMemcpyDeviceToHost, s_out));
-        CU_TRY(h, cudaEventRecord(w.ev_out, s_out));
+        if (io.flat) {
+            CU_TRY(h, cudaMemcpyAsync(w.h_ev_off, w.ev_off, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost, s_out));
+            CU_TRY(h, cudaEventRecord(w.ev_tot, s_out));
+            pend = Pending{&w, e0, n};   // ev_out is recorded by finish_flat()
+        } else {
+            CU_TRY(h, cudaEventRecord(w.ev_out, s_out));
+        }
     }
+    if ((rc = finish_flat())) return rc;
+    if (io.flat && io.pulses_out) io.pulses_out[d] = pool_cur - (int64_t)((__int128)io.pool_cap * lo / io.n_total);
     CU_TRY(h, cudaStreamSynchronize(s_in));
     CU_TRY(h, cudaStreamSynchronize(s_cmp));
     CU_TRY(h, cudaStreamSynchronize(s_out));
@@ -933,6 +1007,8 @@ void npswf_destroy(npswf_handle *h)
             if (s.ws[i].ev_in) cudaEventDestroy(s.ws[i].ev_in);
             if (s.ws[i].ev_cmp) cudaEventDestroy(s.ws[i].ev_cmp);
             if (s.ws[i].ev_out) cudaEventDestroy(s.ws[i].ev_out);
+            if (s.ws[i].ev_tot) cudaEventDestroy(s.ws[i].ev_tot);
+            if (s.ws[i].h_ev_off) cudaFreeHost(s.ws[i].h_ev_off);
         }
         for (int i = 0; i < 4; i++) {
             if (s.fit_stream[i]) cudaStreamDestroy(s.fit_stream[i]);
@@ -1037,6 +1113,35 @@ int npswf_analyze_batch(npswf_handle *h, int64_t n_events, const double *signal,
     io.wfampl = wfampl; io.chi2 = chi2; io.timewf = timewf; io.amplwf = amplwf; io.status = status;
     rc = for_each_slot_range(h, n_events, [&](int d, int64_t lo, int64_t hi) { return analyze_range(h, d, lo, hi, io); });
     if (rc) return rc;
+    h->host_ctr.n_events += n_events;
+    h->host_ctr.n_block_waveforms += n_events * B;
+    return 0;
+}
+
+int npswf_analyze_batch_flat(npswf_handle *h, int64_t n_events, const double *signal, const int32_t *pres,
+                             const double *corr_time_HMS, int32_t *wfnpulse, int64_t *pulse_offset, int32_t *pulse_count,
+                             double *wftime_pool, double *wfampl_pool, int64_t pool_capacity, double *chi2, double *timewf,
+                             double *amplwf, uint8_t *status, int64_t *n_pulses)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (n_events < 0 || pool_capacity < 0 ||
+        (n_events > 0 && (!signal || !pres || !pulse_offset || !pulse_count || !wftime_pool || !wfampl_pool))) {
+        h->err = "npswf_analyze_batch_flat: bad arguments";
+        return NPSWF_ERR_ARG;
+    }
+    if (n_pulses) *n_pulses = 0;
+    if (n_events == 0) return 0;
+    std::vector<int64_t> per_dev(h->slots.size(), 0);
+    HostIO io;
+    io.signal = signal; io.pres = pres; io.corr = corr_time_HMS; io.wfnpulse = wfnpulse; io.chi2 = chi2; io.timewf = timewf;
+    io.amplwf = amplwf; io.status = status;
+    io.flat = true; io.pulse_offset = pulse_offset; io.pulse_count = pulse_count; io.pool_t = wftime_pool; io.pool_a = wfampl_pool;
+    io.pool_cap = pool_capacity; io.n_total = n_events; io.pulses_out = per_dev.data();
+    rc = for_each_slot_range(h, n_events, [&](int d, int64_t lo, int64_t hi) { return analyze_range(h, d, lo, hi, io); });
+    if (rc) return rc;
+    if (n_pulses)
+        for (int64_t v : per_dev) *n_pulses += v;
     h->host_ctr.n_events += n_events;
     h->host_ctr.n_block_waveforms += n_events * B;
     return 0;

@@ -497,3 +497,38 @@ def test_host_packing_is_lossless_and_falls_back(pkg, calib, events):
     d = h.analyze(s3, pres, corr)
     for k in c:
         assert np.array_equal(c[k], d[k]), k
+
+
+def test_flat_outputs_equal_reference_packing(pkg, calib, events):
+    """npswf_analyze_batch_flat: wfampl / wftime packed on the device exactly as the reference packs them
+    (T2:959-961, 1289-1296), for one chunk and for many small chunks (deferred pulse copies)."""
+    for cfg in (2, 3):
+        ev = events[cfg]
+        sig, pres, corr = ev["signal"], ev["pres"], ev["corr_time_HMS"]
+        E = sig.shape[0]
+        for chunk in (0, 1):   # 0: default chunking (one chunk here); 1: the smallest chunks the library makes
+            h = pkg.NpsWf(calib, chunk_events=chunk)
+            pad = h.analyze(sig, pres, corr)
+            flat = h.analyze_flat(sig, pres, corr)
+            for k in ("wfnpulse", "chi2", "timewf", "amplwf", "status"):
+                assert np.array_equal(pad[k], flat[k]), k
+            assert flat["n_pulses"] == int(pad["wfnpulse"].sum())
+            assert np.array_equal(flat["pulse_count"], pad["wfnpulse"].sum(axis=1))
+            for e in range(E):
+                ft, fa, boff = pkg.flatten_event(pad["wfnpulse"][e], pad["wftime"][e], pad["wfampl"][e])
+                o, c = int(flat["pulse_offset"][e]), int(flat["pulse_count"][e])
+                assert c == len(ft)
+                assert np.array_equal(flat["wftime_pool"][o:o + c], ft)
+                assert np.array_equal(flat["wfampl_pool"][o:o + c], fa)
+            # exact-size pool works, one pulse less is refused with a message
+            need = flat["n_pulses"]
+            tight = h.analyze_flat(sig, pres, corr, capacity=need)
+            assert np.array_equal(tight["wftime_pool"], flat["wftime_pool"][:need])
+            with pytest.raises(pkg.NpsWfError) as ei:
+                h.analyze_flat(sig, pres, corr, capacity=need - 1)
+            assert "pool too small" in str(ei.value)
+            again = h.analyze_flat(sig, pres, corr)     # the handle is usable after the refusal
+            assert np.array_equal(again["wftime_pool"][:need], flat["wftime_pool"][:need])
+    # no block present: empty vectors
+    z = h.analyze_flat(sig[:2], np.zeros((2, 1080), np.int32), corr[:2])
+    assert z["n_pulses"] == 0 and (z["pulse_count"] == 0).all()
