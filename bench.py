@@ -324,6 +324,30 @@ def main():
                                     "h2d_bytes_per_step": int(host_in), "d2h_bytes_per_step": int(d2h),
                                     "ms_per_step": 1e3 * float(te.item()) / args.e2e_steps,
                                     "input": "same call, npswf_set_host_packing(0): PCIe-bound"}
+        # the same analysis through npswf_analyze_batch_flat: wfampl / wftime come back in the reference's truncated
+        # layout (T2:1289-1296), packed on the device -- a fraction of the D2H bytes, no flatten pass on the host
+        hf = h.alloc_flat_outputs(Ee, Ee * NB * 4, pinned=True)
+        h.analyze_flat(hs, hp, hc, out=hf)
+        h.reset_counters()
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            h.analyze_flat(hs, hp, hc, out=hf)
+        torch.cuda.synchronize()
+        dtf = time.perf_counter() - t0
+        cf = h.counters()
+        te = torch.tensor([dtf], dtype=torch.float64, device=dev)
+        ce = torch.tensor([cf["n_fit_attempted"]], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ce, op=dist.ReduceOp.SUM)
+        fixed = sum(hf[k].nbytes for k in ("wfnpulse", "chi2", "timewf", "amplwf", "status"))
+        e2e["flat_outputs"] = {"value": float(ce.item()) / float(te.item()), "unit": UNIT,
+                               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(fixed + 16 * hf["n_pulses"] + 4 * Ee),
+                               "ms_per_step": 1e3 * float(te.item()) / args.e2e_steps,
+                               "input": "same f64 host input; npswf_analyze_batch_flat (pulses packed on the device)"}
+        del hf
         # the same call with the int16 ADC-count ABI (exact on the 1000/4096 mV lattice): 4x less PCIe traffic in
         hk = pkg.pinned_empty((Ee, NB, NT), np.int16)
         hk[...] = np.rint(hs / synth.LSB).astype(np.int16)

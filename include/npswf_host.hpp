@@ -46,10 +46,41 @@ public:
     std::vector<EventResult> analyze(int64_t n_events, const double *signal, const int32_t *pres,
                                      const double *corr_time_HMS)
     {
-        Padded p(n_events);
-        check(npswf_analyze_batch(h_, n_events, signal, pres, corr_time_HMS, p.n.data(), p.t.data(), p.a.data(), p.c.data(),
-                                  p.tw.data(), p.aw.data(), p.st.data()));
-        return flatten(n_events, p);
+        // wfampl / wftime arrive already packed the reference's way (npswf_analyze_batch_flat): pools sized for 4 pulses
+        // per block on average first, for the 12-per-block maximum if that was not enough
+        const size_t nb = (size_t)n_events * NPSWF_NBLOCKS;
+        std::vector<int32_t> n(nb), cnt((size_t)n_events);
+        std::vector<int64_t> off((size_t)n_events);
+        std::vector<double> c(nb), tw(nb), aw(nb), pt, pa;
+        for (int64_t per_block : {4, (int)NPSWF_MAXWFPULSES}) {
+            pt.resize(nb * (size_t)per_block);
+            pa.resize(pt.size());
+            const int rc = npswf_analyze_batch_flat(h_, n_events, signal, pres, corr_time_HMS, n.data(), off.data(), cnt.data(),
+                                                    pt.data(), pa.data(), (int64_t)pt.size(), c.data(), tw.data(), aw.data(),
+                                                    nullptr, nullptr);
+            if (rc == NPSWF_ERR_NOMEM && per_block < (int)NPSWF_MAXWFPULSES) continue;
+            check(rc);
+            break;
+        }
+        std::vector<EventResult> out((size_t)n_events);
+        for (int64_t e = 0; e < n_events; e++) {
+            EventResult &r = out[(size_t)e];
+            const size_t o = (size_t)e * NPSWF_NBLOCKS;
+            r.chi2.assign(c.begin() + o, c.begin() + o + NPSWF_NBLOCKS);
+            r.timewf.assign(tw.begin() + o, tw.begin() + o + NPSWF_NBLOCKS);
+            r.amplwf.assign(aw.begin() + o, aw.begin() + o + NPSWF_NBLOCKS);
+            r.wfnpulse.assign(n.begin() + o, n.begin() + o + NPSWF_NBLOCKS);
+            r.blockOffset.resize(NPSWF_NBLOCKS + 1);
+            int32_t run = 0;
+            for (int b = 0; b < NPSWF_NBLOCKS; b++) {   // T2:959-961
+                r.blockOffset[b] = run;
+                run += r.wfnpulse[b];
+            }
+            r.blockOffset[NPSWF_NBLOCKS] = run;          // T2:1022
+            r.wftime.assign(pt.begin() + off[e], pt.begin() + off[e] + cnt[e]);
+            r.wfampl.assign(pa.begin() + off[e], pa.begin() + off[e] + cnt[e]);
+        }
+        return out;
     }
 
     // The same, fed with what the reference's analyze receives (T2:540): the packed branch

@@ -27,7 +27,52 @@ int main()
     npswf::Analyzer an(cfg, cal);
     std::vector<double> mfy(B * NPSWF_MFWIDTH), mfi(B);
     if (npswf_get_mf_calib(an.raw(), mfy.data(), mfi.data()) != 0 || !(mfi[0] > 0)) return 2;
-    if (npswf_device_count() > 0) { std::puts("gpu present: skipping the no-fallback check"); return 0; }
+    if (npswf_device_count() > 0) {
+        // GPU present: the mirror's analyze() (flat outputs packed on the device) must equal the padded C entry point
+        // followed by the host-side packing npswf_flatten_event, event by event
+        const int E = 5;
+        const double lsb = 1000.0 / 4096;
+        std::vector<double> sig((size_t)E * B * T), corr(E);
+        std::vector<int32_t> pres((size_t)E * B, 1);
+        for (int e = 0; e < E; e++) {
+            corr[e] = 0.25 * e;
+            for (int b = 0; b < B; b++)
+                for (int it = 0; it < T; it++) {
+                    const int sh = (b * 7 + e * 3) % 11 - 5;
+                    const int src = it - sh;
+                    double v = 0.4 * (((b * 131 + it * 17 + e * 29) % 7) - 3);                      // pedestal wiggle
+                    if ((b + e) % 3 != 2 && src >= 0 && src < T) v += (15.0 + (b % 23)) * Y[b * T + src];  // one pulse
+                    if ((b + e) % 5 == 0 && src + 14 >= 0 && src + 14 < T) v += 9.0 * Y[b * T + src + 14]; // pile-up
+                    sig[((size_t)e * B + b) * T + it] = std::nearbyint(v / lsb) * lsb;
+                }
+        }
+        auto res = an.analyze(E, sig.data(), pres.data(), corr.data());
+        const size_t nb = (size_t)E * B;
+        std::vector<int32_t> n(nb);
+        std::vector<double> t(nb * NPSWF_MAXWFPULSES), a(nb * NPSWF_MAXWFPULSES), c(nb), tw(nb), aw(nb);
+        std::vector<uint8_t> st(nb);
+        if (npswf_analyze_batch(an.raw(), E, sig.data(), pres.data(), corr.data(), n.data(), t.data(), a.data(), c.data(),
+                                tw.data(), aw.data(), st.data()) != 0) return 4;
+        long long pulses = 0;
+        for (int e = 0; e < E; e++) {
+            std::vector<double> ft((size_t)B * NPSWF_MAXWFPULSES), fa(ft.size());
+            std::vector<int32_t> bo(B + 1);
+            const size_t o = (size_t)e * B;
+            const int64_t tot = npswf_flatten_event(&n[o], &t[o * NPSWF_MAXWFPULSES], &a[o * NPSWF_MAXWFPULSES], ft.data(),
+                                                    fa.data(), bo.data());
+            const npswf::EventResult &r = res[e];
+            if ((int64_t)r.wftime.size() != tot || (int64_t)r.wfampl.size() != tot) return 5;
+            for (int64_t i = 0; i < tot; i++)
+                if (r.wftime[i] != ft[i] || r.wfampl[i] != fa[i]) return 6;
+            for (int b = 0; b <= B; b++)
+                if (r.blockOffset[b] != bo[b]) return 7;
+            for (int b = 0; b < B; b++)
+                if (r.wfnpulse[b] != n[o + b] || r.chi2[b] != c[o + b] || r.timewf[b] != tw[o + b] || r.amplwf[b] != aw[o + b]) return 8;
+            pulses += tot;
+        }
+        std::printf("gpu present: mirror analyze() == C entry point + flatten on %d events, %lld pulses\n", E, pulses);
+        return pulses > 1000 ? 0 : 9;
+    }
     std::vector<double> sig((size_t)B * T, 0.0), corr(1, 0.0);
     std::vector<int32_t> pres(B, 1);
     int refused = 0;

@@ -6,6 +6,8 @@ bin contents and the cluster-threshold decision; for blocks where both fits conv
 |dt| <= 0.01 bin, |dA|/A <= 1e-3, relative chi2 <= 1e-3.  The reference minimiser (Migrad) and the
 GPU minimiser (analytic LM) are different algorithms, so on multi-pulse blocks a small fraction
 lands in a different local minimum of the same chi2; the tests state and bound that fraction."""
+import os
+
 import numpy as np
 import pytest
 
@@ -532,3 +534,17 @@ def test_flat_outputs_equal_reference_packing(pkg, calib, events):
     # no block present: empty vectors
     z = h.analyze_flat(sig[:2], np.zeros((2, 1080), np.int32), corr[:2])
     assert z["n_pulses"] == 0 and (z["pulse_count"] == 0).all()
+
+
+def test_cpp_host_mirror_on_gpu(tmp_path, pkg):
+    """The C++ mirror (include/npswf_host.hpp): analyze() through the device-packed flat outputs equals the padded
+    C entry point + npswf_flatten_event (tests/cpp/host_mirror_smoke.cpp, GPU branch)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "host_mirror_smoke")
+    libdir = os.path.dirname(pkg.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "host_mirror_smoke.cpp"), "-o", exe,
+                           "-L", libdir, "-lnpswf", "-Wl,-rpath," + libdir])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "gpu present" in r.stdout, r.stdout + r.stderr
