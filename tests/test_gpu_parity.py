@@ -548,3 +548,99 @@ def test_cpp_host_mirror_on_gpu(tmp_path, pkg):
                            "-L", libdir, "-lnpswf", "-Wl,-rpath," + libdir])
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "gpu present" in r.stdout, r.stdout + r.stderr
+
+
+def test_blocks_without_reference_waveform(pkg, calib, events):
+    """preswf == 0 blocks (no ref_wf file, T2:452-456): never analysed (T2:944), but their samples still enter the
+    3x3 sums of their neighbours, whose gate is pres alone (T2:257)."""
+    cal = dict(calib)
+    rng = np.random.default_rng(5)
+    preswf = np.ones(1080, np.int32)
+    preswf[rng.choice(1080, 60, replace=False)] = 0
+    cal["preswf"] = preswf
+    o = oracle.Oracle(cal)
+    h = pkg.NpsWf(cal)
+    ev = events[2]
+    ref = o.analyze_batch(ev["signal"], ev["pres"], ev["corr_time_HMS"], n_threads=8)
+    got = h.analyze(ev["signal"], ev["pres"], ev["corr_time_HMS"])
+    off = preswf == 0
+    assert (got["wfnpulse"][:, off] == 0).all() and (got["chi2"][:, off] == -100).all() and (got["status"][:, off] == 0).all()
+    assert np.array_equal(got["wfnpulse"], ref["wfnpulse"])
+    assert np.array_equal(got["status"] & 3, ref["status"] & 3)
+    nofit = (ref["status"] & 28) == 0
+    for k in ("wftime", "wfampl", "chi2", "timewf", "amplwf"):
+        assert np.array_equal(got[k][nofit], ref[k][nofit]), k
+    n_both, frac, _, _ = _fit_agreement(ref, got)
+    assert n_both > 1000 and frac >= 0.99
+    # a 6 mV pulse next to an 8 mV pulse in a switched-off block: passes the 10 mV threshold only through the
+    # neighbour's samples, which count as long as the neighbour is present in the data (pres), preswf or not
+    bx = int(np.flatnonzero(off)[np.flatnonzero(off) % 30 > 0][0])    # a switched-off block with a left neighbour
+    lsb = synth.LSB
+    sig = np.zeros((1, 1080, 110))
+    sig[0, bx - 1] = np.round(6.0 * calib["interpY"][bx - 1] / lsb) * lsb
+    sig[0, bx] = np.round(8.0 * calib["interpY"][bx] / lsb) * lsb
+    pres1 = np.zeros((1, 1080), np.int32)
+    pres1[0, bx - 1] = pres1[0, bx] = 1
+    for pres_nb, expect in ((1, 2), (0, 0)):
+        pres1[0, bx] = pres_nb
+        r = o.analyze_batch(sig, pres1, np.zeros(1), n_threads=1)
+        g = h.analyze(sig, pres1, np.zeros(1))
+        assert (r["status"][0, bx - 1] & 2) == expect and (g["status"][0, bx - 1] & 2) == expect
+        assert g["status"][0, bx] == 0 and g["wfnpulse"][0, bx] == 0
+        assert np.array_equal(g["wfnpulse"], r["wfnpulse"])
+
+
+def test_full_size_configs_by_properties(pkg, calib):
+    """BASELINE configs[1] (100 000 events, 1-3 pulses) and configs[2] (10 000 events, up to 12 pulses) at full size,
+    generated on the device in slices: the bookkeeping identities hold, the results do not depend on how the events
+    are cut into chunks (bitwise, whole output arrays compared on the device), and the rates that the configurations
+    are designed to produce are there (every block fitted in config 2; peak-buffer-full and fall-backs in config 3)."""
+    import torch
+    dev = torch.device("cuda:0")
+    ha = pkg.NpsWf(calib)                      # default chunks (1 184 events)
+    hb = pkg.NpsWf(calib, chunk_events=444)    # other chunking
+    stream = torch.cuda.Stream()
+    st = stream.cuda_stream
+    d_spl = torch.from_numpy(ha.spline_coeffs()).to(dev)
+    d_tref = torch.from_numpy(calib["timeref"]).to(dev)
+    d_kap = torch.from_numpy(calib["kappa"]).to(dev)
+    names = (("wfnpulse", torch.int32, ()), ("wftime", torch.float64, (12,)), ("wfampl", torch.float64, (12,)),
+             ("chi2", torch.float64, ()), ("timewf", torch.float64, ()), ("amplwf", torch.float64, ()),
+             ("status", torch.uint8, ()))
+    for cfg, total, slice_events in ((2, 100_000, 12_500), (3, 10_000, 5_000)):
+        sig = torch.empty((slice_events, 1080, 110), dtype=torch.float64, device=dev)
+        pres = torch.empty((slice_events, 1080), dtype=torch.int32, device=dev)
+        corr = torch.empty((slice_events,), dtype=torch.float64, device=dev)
+        oa = {k: torch.empty((slice_events, 1080) + sh, dtype=dt, device=dev) for k, dt, sh in names}
+        ob = {k: torch.empty((slice_events, 1080) + sh, dtype=dt, device=dev) for k, dt, sh in names}
+        ha.reset_counters()
+        n_fitted = n_pulses = n_pass = 0
+        for first in range(0, total, slice_events):
+            synth.generate_device(synth.config_params(cfg), d_spl.data_ptr(), d_tref.data_ptr(), d_kap.data_ptr(), first,
+                                  slice_events, sig.data_ptr(), 0, pres.data_ptr(), corr.data_ptr(), st)
+            for h, o in ((ha, oa), (hb, ob)):
+                h.analyze_device(slice_events, sig.data_ptr(), pres.data_ptr(), corr.data_ptr(), o["wfnpulse"].data_ptr(),
+                                 o["wftime"].data_ptr(), o["wfampl"].data_ptr(), o["chi2"].data_ptr(),
+                                 o["timewf"].data_ptr(), o["amplwf"].data_ptr(), o["status"].data_ptr(), stream=st)
+                h.sync_device(stream=st)
+            torch.cuda.synchronize()
+            for k, _, _ in names:
+                assert torch.equal(oa[k], ob[k]), "cfg %d slice %d: %s depends on the chunking" % (cfg, first, k)
+            fitted = (oa["status"] & 28) > 0
+            assert torch.equal(fitted, ((oa["status"] & 2) > 0) & (oa["wfnpulse"] > 0))
+            assert bool(((oa["chi2"] == -100.0) == ((oa["status"] & 12) == 0)).all())     # chi2 sentinel <=> no converged fit
+            assert int(oa["wfnpulse"].max()) <= 12 and int(oa["wfnpulse"].min()) >= 0
+            n_fitted += int(fitted.sum()); n_pulses += int(oa["wfnpulse"].sum()); n_pass += int(((oa["status"] & 2) > 0).sum())
+        c = ha.counters()
+        assert c["n_block_waveforms"] == total * 1080 and c["n_present"] == total * 1080
+        assert c["n_fit_attempted"] == n_fitted == c["n_fit_ok_first"] + c["n_fit_ok_retry"] + c["n_fallback"]
+        assert c["n_pulses"] == n_pulses and c["n_pass_threshold"] == n_pass
+        print("cfg%d full size: %d events, fitted %.4f of the blocks, %.3f pulses per fitted block, fall-backs %d, "
+              "peak buffer full %d" % (cfg, total, n_fitted / (total * 1080.0), n_pulses / max(1, n_fitted),
+                                       c["n_fallback"], c["n_peak_buffer_full"]))
+        if cfg == 2:
+            assert n_fitted > 0.999 * total * 1080 and c["n_fallback"] < 1e-3 * n_fitted
+        else:
+            assert c["n_peak_buffer_full"] > 0 and c["n_fallback"] + c["n_fit_ok_retry"] > 0
+        del sig, pres, corr, oa, ob
+        torch.cuda.empty_cache()
