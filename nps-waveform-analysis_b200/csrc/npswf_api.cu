@@ -597,6 +597,8 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
                 const double a = 48.0e9 / s.pack_rate;
                 f = std::min(1.0, std::max(0.0, (a - 0.25) / (a + 0.75)));
                 if (f > 0.9) f = 1.0;
+            } else if (h->pack_mode == 1 && s.pack_rate < 10.0e9) {
+                f = 1.0;   // pageable source and one or two slow host threads: the driver's staged upload is no slower
             }
             n_raw = std::min<int64_t>(n, (int64_t)(f * (double)n + 0.5));
         }
