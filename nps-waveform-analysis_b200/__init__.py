@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libnpswf.so")
+LIB_PATH = os.environ.get("NPSWF_LIB") or os.path.join(_HERE, "lib", "libnpswf.so")   # NPSWF_LIB: A/B builds of the same ABI
 
 NTIME, NCOL, NLIN, NBLOCKS, MAXWFPULSES, MFWIDTH = 110, 30, 36, 1080, 12, 11
 ST_PRESENT, ST_OKTOFIT, ST_FIT_OK1, ST_FIT_OK2, ST_FALLBACK = 1, 2, 4, 8, 16
