@@ -106,6 +106,7 @@ struct npswf_handle {
     std::mutex mu;
     bool profiling = false;
     int pack_mode = 1;                 // 0 off, 1 auto (on while it is faster than the raw upload), 2 always
+    bool chunk_ramp = true;            // env NPSWF_CHUNK_RAMP=0: equal chunks in the host pipeline
     int pack_threads = 0;              // host threads per device
     double pack_lsb = 1000.0 / 4096;   // ADCtomV, T2:357
     double stage_ms[3] = {0, 0, 0};  // front, search, fit
@@ -585,9 +586,28 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
     };
     int which = 0;
     int64_t k = 0;
-    for (int64_t e0 = lo; e0 < hi; e0 += chunk, which ^= 1, k++) {
+    // The pipeline is empty while the first chunk is packed and uploaded and while the last one is downloaded: the
+    // first chunks ramp up (a quarter, then half of the regular size) and the last one is half a chunk when the call
+    // is long enough for that to pay (a small chunk uses the kernels less well).
+    std::vector<int64_t> cuts;   // chunk k = events [cuts[k], cuts[k+1])
+    {
+        const int64_t unit = 148, q = std::max<int64_t>(unit, chunk / 4 / unit * unit), hf = std::max<int64_t>(unit, chunk / 2 / unit * unit);
+        int64_t e = lo;
+        cuts.push_back(e);
+        if (hi - lo >= 6 * chunk && chunk >= 2 * unit && h->chunk_ramp) {
+            e += q; cuts.push_back(e);
+            e += hf; cuts.push_back(e);
+            while (hi - e > chunk + hf) { e += chunk; cuts.push_back(e); }
+            if (hi - e > hf) { e = hi - hf; cuts.push_back(e); }
+        } else {
+            while (hi - e > chunk) { e += chunk; cuts.push_back(e); }
+        }
+        cuts.push_back(hi);
+    }
+    for (size_t ci = 0; ci + 1 < cuts.size(); ci++, which ^= 1, k++) {
+        const int64_t e0 = cuts[ci];
         Workspace &w = s.ws[which];
-        const int64_t n = std::min<int64_t>(chunk, hi - e0);
+        const int64_t n = cuts[ci + 1] - e0;
         const size_t nb = (size_t)n * B, ob = (size_t)e0 * B;
         // events [0, n_raw) of the chunk travel as doubles, [n_raw, n) as counts
         int64_t n_raw = n;
@@ -786,6 +806,7 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
         if (getenv("NPSWF_HOST_PACK_THREADS") && atoi(getenv("NPSWF_HOST_PACK_THREADS")) > 0)
             h->pack_threads = atoi(getenv("NPSWF_HOST_PACK_THREADS"));
         if (getenv("NPSWF_HOST_PACK")) h->pack_mode = std::min(2, std::max(0, atoi(getenv("NPSWF_HOST_PACK"))));
+        if (getenv("NPSWF_CHUNK_RAMP")) h->chunk_ramp = atoi(getenv("NPSWF_CHUNK_RAMP")) != 0;
     }
     // ---- derived calibration on the host (T2:440-451 for mfyref/mfint; spline coefficients)
     h->mfyref.assign((size_t)B * MFW, 0.0);
