@@ -35,6 +35,8 @@ __attribute__((target("avx2"))) bool pack_avx2(const double *__restrict__ x, int
     const __m256d vhi = _mm256_set1_pd(32767.0), vlo = _mm256_set1_pd(-32767.0);
     __m256d inr = _mm256_castsi256_pd(_mm256_set1_epi64x(-1));   // all ones while every sample is reproduced and in range
     size_t i = 0;
+    // the staging buffer is written once and read by the copy engine only: streaming stores (no read-for-ownership)
+    const bool stream = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
     for (; i + 8 <= n; i += 8) {
         const __m256d a = _mm256_loadu_pd(x + i), b = _mm256_loadu_pd(x + i + 4);
         const __m256d ka = _mm256_sub_pd(_mm256_add_pd(_mm256_mul_pd(a, vinv), vmagic), vmagic);
@@ -45,8 +47,10 @@ __attribute__((target("avx2"))) bool pack_avx2(const double *__restrict__ x, int
         inr = _mm256_and_pd(inr, _mm256_and_pd(_mm256_cmp_pd(kb, vhi, _CMP_LE_OQ), _mm256_cmp_pd(kb, vlo, _CMP_GE_OQ)));
         // out-of-range lanes convert to INT_MIN and saturate: harmless, the chunk is rejected anyway
         const __m128i ia = _mm256_cvtpd_epi32(ka), ib = _mm256_cvtpd_epi32(kb);
-        _mm_storeu_si128(reinterpret_cast<__m128i *>(out + i), _mm_packs_epi32(ia, ib));
+        if (stream) _mm_stream_si128(reinterpret_cast<__m128i *>(out + i), _mm_packs_epi32(ia, ib));
+        else _mm_storeu_si128(reinterpret_cast<__m128i *>(out + i), _mm_packs_epi32(ia, ib));
     }
+    if (stream) _mm_sfence();
     bool ok = _mm256_movemask_pd(inr) == 0xf;
     if (i < n) ok = pack_portable(x + i, out + i, n - i, lsb, inv_lsb) && ok;
     return ok;

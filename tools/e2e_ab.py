@@ -1,3 +1,4 @@
+"""A/B probe of the host-buffer entry points (f64 with / without the int16 transport, int16 ABI): best and median of 5 calls."""
 import importlib, os, sys, time
 import numpy as np
 sys.path.insert(0, os.getcwd())
@@ -22,4 +23,4 @@ for name, mode, fn in (("f64 auto", 1, lambda: h.analyze(hs, hp, hc, out=ho)), (
     ts = []
     for _ in range(5):
         t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
-    print("ramp=%s %-9s best %.1f ms median %.1f ms -> %.1f M/s" % (os.environ.get("NPSWF_CHUNK_RAMP", "1"), name, min(ts) * 1e3, sorted(ts)[2] * 1e3, E * 1080 / sorted(ts)[2] / 1e6), flush=True)
+    print("ramp=%s %-9s best %.1f ms median %.1f ms -> %.1f M/s" % (os.environ.get("NPSWF_CHUNK_RAMP", "1"), name, min(ts) * 1e3, sorted(ts)[2] * 1e3, E * 1080 / sorted(ts)[2] / 1e6), h.host_packing_stats(), flush=True)
