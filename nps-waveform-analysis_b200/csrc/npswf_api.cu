@@ -503,7 +503,8 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
     int rc = ensure_io(h, s);
     if (rc) return rc;
     // Host buffers: a three-stage pipeline over the two workspaces -- uploads on their own stream, every kernel on
-    // one compute stream (two chunks computing side by side would only fight for shared memory), downloads on a
+    // one compute stream (measured: with the chunks' kernels on two streams, as in the device path, they interleave, every
+    // chunk finishes later and its download and the next upload with it: 61.8 instead of 54.2 ms per 4 736 events), downloads on a
     // third stream -- so the copy engines of both directions run under the kernels of the neighbouring chunks.
     // Eight to twelve chunks per call (multiples of 148 events, at least 296) keep the uncovered first upload and
     // last download short.
