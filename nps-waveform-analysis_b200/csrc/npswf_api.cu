@@ -90,6 +90,7 @@ struct DevSlot {
     int64_t packed_chunks = 0, raw_chunks = 0;
     double pack_seconds = 0, pack_bytes = 0;
     double pack_rate = 0;                                    // running estimate, bytes of doubles per second
+    bool pack_unavailable = false;                           // the pinned staging buffers could not be allocated
 };
 
 }  // namespace
@@ -519,22 +520,33 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
     // mode the first n_raw events of every chunk are uploaded as they are while the host packs the rest, with the
     // split chosen so that both finish together -- (1-f) / pack_rate = (f + (1-f)/4) / dma_rate.  From pageable memory
     // the raw upload is slow and blocks the caller, so everything is packed.
-    const bool pack = io.signal && !io.counts && !io.packed && h->pack_mode != 0;
+    bool pack = io.signal && !io.counts && !io.packed && h->pack_mode != 0 && !s.pack_unavailable;
     bool pinned_src = false;
     if (pack) {
         if (!s.packer) s.packer.reset(new PackPool(h->pack_threads));
         const size_t need = (size_t)std::min<int64_t>(chunk, hi - lo) * B * T;
         if (need > s.stage_cap) {
-            for (int i = 0; i < 3; i++) {
+            s.stage_cap = 0;
+            for (int i = 0; i < 3 && pack; i++) {
                 if (s.stage_busy[i]) CU_TRY(h, cudaEventSynchronize(s.stage_ev[i]));
                 s.stage_busy[i] = false;
                 if (s.stage[i]) CU_TRY(h, cudaFreeHost(s.stage[i]));
                 s.stage[i] = nullptr;
-                CU_TRY(h, cudaHostAlloc((void **)&s.stage[i], need * sizeof(int16_t), cudaHostAllocPortable));
                 if (!s.stage_ev[i]) CU_TRY(h, cudaEventCreateWithFlags(&s.stage_ev[i], cudaEventDisableTiming));
+                if (cudaHostAlloc((void **)&s.stage[i], need * sizeof(int16_t), cudaHostAllocPortable) != cudaSuccess) {
+                    // no pinned memory for the staging buffers: this is a transport optimisation, not a requirement --
+                    // the traces go over as the caller's doubles from now on
+                    (void)cudaGetLastError();
+                    s.stage[i] = nullptr;
+                    for (int j = 0; j < i; j++) { cudaFreeHost(s.stage[j]); s.stage[j] = nullptr; }
+                    s.pack_unavailable = true;
+                    pack = false;
+                }
             }
-            s.stage_cap = need;
+            if (pack) s.stage_cap = need;
         }
+    }
+    if (pack) {
         cudaPointerAttributes at{};
         pinned_src = cudaPointerGetAttributes(&at, io.signal) == cudaSuccess && at.type == cudaMemoryTypeHost;
         (void)cudaGetLastError();
