@@ -15,6 +15,12 @@ constexpr int MFW = NPSWF_MFWIDTH;    // 11                   T2:67
 constexpr int MFLEFT = 5, MFRIGHT = 5;   //                   T2:65-66
 constexpr int MFSTART = 10, MFEND = 100; //                   T2:68-69
 constexpr int NFIT = MFEND - MFSTART;    // 90 fit points     T2:681
+// Convergence tolerance of every fit kernel: stop when a step lowered chi2 by less than FIT_REL_TOL * chi2, or when the
+// Gauss-Newton bound of what the next step could gain is below it.
+#ifndef NPSWF_FIT_REL_TOL
+#define NPSWF_FIT_REL_TOL 1e-9
+#endif
+constexpr double FIT_REL_TOL = NPSWF_FIT_REL_TOL;
 constexpr int MAXPAR = 2 * MAXP + 1;     // 25
 
 constexpr int ROW_DOUBLES = NCOL * T;              // one detector row of traces

@@ -264,7 +264,7 @@ fit_kernel(const int *__restrict__ job_list, const int *__restrict__ job_count, 
         }
         __syncwarp();
         LmOutcome r = {false, 0.0, first_attempt_iters};
-        if (!first_attempt_done) r = lm_warp<PMAX>(sm, N, P, lane, y, w, spl, kp.fit_max_iter, 1e-3, 1e-9);
+        if (!first_attempt_done) r = lm_warp<PMAX>(sm, N, P, lane, y, w, spl, kp.fit_max_iter, 1e-3, FIT_REL_TOL);
         int st = 0;
         int iters = r.iters;
         if (r.ok) st = NPSWF_ST_FIT_OK1;
@@ -276,7 +276,7 @@ fit_kernel(const int *__restrict__ job_list, const int *__restrict__ job_count, 
                 sm->par[2 + 2 * lane] = seed_a;
             }
             __syncwarp();
-            r = lm_warp<PMAX>(sm, N, P, lane, y, w, spl, kp.fit_retry_max_iter, 1.0, 1e-9);
+            r = lm_warp<PMAX>(sm, N, P, lane, y, w, spl, kp.fit_retry_max_iter, 1.0, FIT_REL_TOL);
             iters += r.iters;
             if (r.ok) st = NPSWF_ST_FIT_OK2;
         }

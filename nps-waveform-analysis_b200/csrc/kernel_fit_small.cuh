@@ -231,7 +231,7 @@ fit_small_kernel(const int *__restrict__ job_list, const int *__restrict__ job_c
 {
     constexpr int P = 2 * N + 1;
     constexpr int PTS = 96 / GROUP;
-    constexpr double REL_TOL = 1e-9;
+    constexpr double REL_TOL = FIT_REL_TOL;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int g = lane & (GROUP - 1);

@@ -163,7 +163,7 @@ fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
 {
     constexpr int P = 2 * N + 1;
     constexpr int U = (N == 1) ? 5 : 1;
-    constexpr double REL_TOL = 1e-9;
+    constexpr double REL_TOL = FIT_REL_TOL;
     const unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char ft_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
