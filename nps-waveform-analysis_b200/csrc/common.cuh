@@ -21,6 +21,9 @@ constexpr int NFIT = MFEND - MFSTART;    // 90 fit points     T2:681
 #define NPSWF_FIT_REL_TOL 1e-9
 #endif
 constexpr double FIT_REL_TOL = NPSWF_FIT_REL_TOL;
+// continuation lists of N >= 4: bit 30 of an entry = the first attempt was cut short in fit_thread_kernel and has to be
+// run (again, from the seeds) by the warp-per-fit kernel; without it only the retry is left
+constexpr int FIT_CONT_RESTART = 1 << 30;
 constexpr int MAXPAR = 2 * MAXP + 1;     // 25
 
 constexpr int ROW_DOUBLES = NCOL * T;              // one detector row of traces

@@ -227,7 +227,9 @@ fit_kernel(const int *__restrict__ job_list, const int *__restrict__ job_count, 
     unsigned long long c_ok1 = 0, c_ok2 = 0, c_fb = 0, c_it = 0, c_att = 0;
 
     for (int job = blockIdx.x * FIT_WARPS + warp; job < njobs; job += warps_total) {
-        const long long item = job_list[job];
+        const int raw = job_list[job];
+        const long long item = raw & (FIT_CONT_RESTART - 1);
+        const bool first_done = first_attempt_done && !(raw & FIT_CONT_RESTART);
         const long long e = item / B;
         const int bn = (int)(item % B);
         const double *sig = signal + (size_t)item * T;
@@ -264,7 +266,7 @@ fit_kernel(const int *__restrict__ job_list, const int *__restrict__ job_count, 
         }
         __syncwarp();
         LmOutcome r = {false, 0.0, first_attempt_iters};
-        if (!first_attempt_done) r = lm_warp<PMAX>(sm, N, P, lane, y, w, spl, kp.fit_max_iter, 1e-3, FIT_REL_TOL);
+        if (!first_done) r = lm_warp<PMAX>(sm, N, P, lane, y, w, spl, kp.fit_max_iter, 1e-3, FIT_REL_TOL);
         int st = 0;
         int iters = r.iters;
         if (r.ok) st = NPSWF_ST_FIT_OK1;

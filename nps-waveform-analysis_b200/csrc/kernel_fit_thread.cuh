@@ -170,9 +170,11 @@ fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
     float2 *ywwarp = reinterpret_cast<float2 *>(ft_smem + (size_t)warp * FT_WARP_BYTES);   // [90][33] (sample, 1/err)
     const float2 *ywcol = ywwarp + lane;
     const int njobs = *job_count;
-    // N >= 4 has no sub-warp continuation kernel: the thread runs the whole first attempt (at most fit_max_iter accepted
-    // steps and 30 rejected ones) and hands over only what needs the retry
-    const int max_tries = (N <= 3) ? kp.fit_thread_tries : kp.fit_max_iter + 30;
+    // N >= 4 has no sub-warp continuation kernel that could take over the LM state: a fit that is not done after
+    // fit_thread_tries + 10 tries (a thread's try takes ~30x as long as a warp's, and these kernels have few jobs, so
+    // such a fit would be the tail of the whole stage) is handed to the warp-per-fit kernel, which runs its first
+    // attempt again from the seeds and then the retry
+    const int max_tries = (N <= 3) ? kp.fit_thread_tries : kp.fit_thread_tries + 10;
     unsigned long long c_ok1 = 0, c_it = 0, c_att = 0, c_ev = 0;
 
     bool has_job = false, exhausted = false, fresh = false;
@@ -318,7 +320,9 @@ fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
                 rejects++;
                 if (rejects >= 30) { finished = true; iters++; }  // no descent step left
             }
-            if (!finished && tries >= max_tries) handoff = true;
+            bool restart = false;
+            if (!finished && !handoff && tries >= max_tries) { handoff = true; restart = N >= 4; }
+            if (handoff && restart) item |= FIT_CONT_RESTART;
         }
         if (handoff) {   // continuation record: fit_small_kernel re-evaluates at par and carries on
             const int idx = atomicAdd(cont_count, 1);

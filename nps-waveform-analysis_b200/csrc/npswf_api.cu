@@ -337,7 +337,9 @@ int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, cons
         for (int i = 0; i < 4; i++) CU_TRY(h, cudaStreamWaitEvent(s.fit_stream[i], s.fit_fork, 0));
     }
     for (int N = 1; N <= MAXP; N++) {
-        if (conc) st = s.fit_stream[N <= 3 ? N - 1 : 3];
+        // N = 1, 2, 3 have a stream each; N >= 4 (few jobs, long tails) are dealt round the four streams so that their
+        // tails overlap instead of queueing behind one another
+        if (conc) st = s.fit_stream[(N - 1) % 4];
         const int *list = w.fit_dense + (size_t)N * stride;
         const int *cnt = w.fit_count + N;
         int *next = w.fit_count + 16 + N;  // per-multiplicity job cursor, zeroed with fit_count
