@@ -214,8 +214,10 @@ fit_kernel(const int *__restrict__ job_list, const int *__restrict__ job_count, 
            const double *__restrict__ corr_time_HMS, DevCalib cal, KParams kp, double *__restrict__ wftime,
            double *__restrict__ wfampl, double *__restrict__ chi2_out, double *__restrict__ timewf,
            double *__restrict__ amplwf, uint8_t *__restrict__ status, DeviceCounters *__restrict__ ctr,
-           int first_attempt_done = 0, int first_attempt_iters = 0)
+           int first_attempt_done = 0, int first_attempt_iters = 0, int *__restrict__ job_next = nullptr)
 {
+    // job_next: a zeroed cursor -> jobs are claimed one at a time (the lists this kernel gets are short and their
+    // fits very unequal, so a fixed deal leaves most warps waiting for a few); null -> fixed deal by warp index
     // first_attempt_done: the list holds fits whose first attempt was run (and exhausted) by fit_thread_kernel;
     // only the retry is left to do here
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -226,7 +228,13 @@ fit_kernel(const int *__restrict__ job_list, const int *__restrict__ job_count, 
     const int warps_total = gridDim.x * FIT_WARPS;
     unsigned long long c_ok1 = 0, c_ok2 = 0, c_fb = 0, c_it = 0, c_att = 0;
 
-    for (int job = blockIdx.x * FIT_WARPS + warp; job < njobs; job += warps_total) {
+    for (int job = blockIdx.x * FIT_WARPS + warp;; job += warps_total) {
+        if (job_next) {
+            int j = 0;
+            if (lane == 0) j = atomicAdd(job_next, 1);
+            job = __shfl_sync(0xffffffffu, j, 0);
+        }
+        if (job >= njobs) break;
         const int raw = job_list[job];
         const long long item = raw & (FIT_CONT_RESTART - 1);
         const bool first_done = first_attempt_done && !(raw & FIT_CONT_RESTART);

@@ -78,7 +78,7 @@ struct DevSlot {
     bool fit_thread = true;     // thread-per-fit kernels for N = 1, 2 (env NPSWF_FIT_THREAD=0 selects the sub-warp kernels)
     int occ_fit_thread[5] = {0, 2, 2, 2, 2};   // [4]: N = 4..6
     int fit_thread_maxocc = 0;  // env NPSWF_FIT_THREAD_OCC: cap on resident CTAs per SM (fewer CTAs leave more L1)
-    int occ_front = 2, occ_search = 4, occ_fit_big = 1, occ_fit_small[4] = {0, 4, 4, 2};  // resident CTAs per SM
+    int occ_front = 2, occ_search = 4, occ_fit_big = 1, occ_fit_mid = 2, occ_fit_small[4] = {0, 4, 4, 2};  // resident CTAs per SM
     std::vector<cudaEvent_t> prof_events;  // 4 per profiled chunk: start, after front, after search, after fits
     std::vector<cudaEvent_t> prof_pool;
     // lossless int16 transport of the binary64 host layout (host_pack.hpp): pool, three pinned staging buffers
@@ -384,8 +384,10 @@ int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, cons
                 fit_thread_kernel<6><<<tgrid, FT_THREADS, FT_SMEM, st>>>(list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl,
                                                                         chi2, timewf, amplwf, status, s.ctr, ccnt, clist, nullptr);
             CU_TRY(h, cudaGetLastError());
-            fit_kernel<25><<<s.sm_count * s.occ_fit_big, FIT_THREADS, sizeof(FitSmem<25>) * FIT_WARPS, st>>>(
-                clist, ccnt, N, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, 1, h->kp.fit_max_iter);
+            // P <= 13: half the shared memory of the 25-parameter instance, twice the resident warps; jobs claimed one by one
+            fit_kernel<13><<<s.sm_count * s.occ_fit_mid, FIT_THREADS, sizeof(FitSmem<13>) * FIT_WARPS, st>>>(
+                clist, ccnt, N, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, 1, h->kp.fit_max_iter,
+                w.fit_count + 48 + N);
         } else if (N == 1) {
             fit_small_kernel<1, 8, FS_MINB1><<<s.sm_count * s.occ_fit_small[1], FS_THREADS, 0, st>>>(
                 list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr);
@@ -397,7 +399,7 @@ int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, cons
                 list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr);
         } else {
             fit_kernel<25><<<s.sm_count * s.occ_fit_big, FIT_THREADS, sizeof(FitSmem<25>) * FIT_WARPS, st>>>(
-                list, cnt, N, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr);
+                list, cnt, N, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, 0, 0, next);
         }
         CU_TRY(h, cudaGetLastError());
     }
@@ -994,6 +996,10 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_search, search_kernel, SEARCH_THREADS, SEARCH_SMEM));
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_big, fit_kernel<25>, FIT_THREADS,
                                                          sizeof(FitSmem<25>) * FIT_WARPS));
+        CR(cudaFuncSetAttribute(fit_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(sizeof(FitSmem<13>) * FIT_WARPS)));
+        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_mid, fit_kernel<13>, FIT_THREADS,
+                                                         sizeof(FitSmem<13>) * FIT_WARPS));
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_small[1], fit_small_kernel<1, 8, FS_MINB1>, FS_THREADS, 0));
         s.fit_thread = !(getenv("NPSWF_FIT_THREAD") && atoi(getenv("NPSWF_FIT_THREAD")) == 0);
         CR(cudaFuncSetAttribute(fit_thread_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
@@ -1019,7 +1025,7 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
         if (s.occ_fit_thread[1] < 1 || s.occ_fit_thread[2] < 1 || s.occ_fit_thread[3] < 1) { h->err = "fit_thread_kernel does not fit on this device"; return fail(NPSWF_ERR_CUDA); }
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_small[2], fit_small_kernel<2, 8, FS_MINB2>, FS_THREADS, 0));
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_small[3], fit_small_kernel<3, 16, FS_MINB3>, FS_THREADS, 0));
-        if (s.occ_front < 1 || s.occ_search < 1 || s.occ_fit_big < 1 || s.occ_fit_small[1] < 1 ||
+        if (s.occ_front < 1 || s.occ_search < 1 || s.occ_fit_big < 1 || s.occ_fit_mid < 1 || s.occ_fit_small[1] < 1 ||
             s.occ_fit_small[2] < 1 || s.occ_fit_small[3] < 1) {
             h->err = "a kernel does not fit on this device (occupancy 0)";
             return fail(NPSWF_ERR_CUDA);

@@ -1,3 +1,4 @@
+"""A/B aid: compare two dumps of tools/ab_dump.py (gpurun_out/ab_old.npz, gpurun_out/ab_new.npz)."""
 import numpy as np
 a=np.load("gpurun_out/ab_old.npz"); b=np.load("gpurun_out/ab_new.npz")
 sa,sb=a["status"],b["status"]

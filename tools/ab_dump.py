@@ -1,3 +1,4 @@
+"""A/B aid: dump status / chi2 / wfnpulse of 592 device-generated config-3 events for the library selected by NPSWF_LIB."""
 import importlib, os, sys
 import numpy as np
 sys.path.insert(0, os.getcwd())
@@ -18,4 +19,4 @@ h.analyze_device(E, sig.data_ptr(), pres.data_ptr(), corr.data_ptr(), o["wfnpuls
                  o["chi2"].data_ptr(), o["timewf"].data_ptr(), o["amplwf"].data_ptr(), o["status"].data_ptr(), stream=st)
 h.sync_device(stream=st); torch.cuda.synchronize()
 print(tag, {k: v for k, v in h.counters().items() if "fit" in k or "fallback" in k})
-np.savez("gpurun_out/ab_%s.npz" % tag, status=o["status"].cpu().numpy(), chi2=o["chi2"].cpu().numpy(), n=o["wfnpulse"].cpu().numpy(), t=o["wftime"].cpu().numpy())
+np.savez("gpurun_out/ab_%s.npz" % tag, status=o["status"].cpu().numpy(), chi2=o["chi2"].cpu().numpy(), n=o["wfnpulse"].cpu().numpy())
