@@ -459,6 +459,15 @@ def test_two_devices_in_one_process_equal_one_device(pkg, calib, spline):
         assert np.array_equal(one[k], two[k]), k
     c = h2.counters()
     assert c["n_events"] == E and c["n_fit_attempted"] == int(((one["status"] & 28) > 0).sum())
+    assert h2.host_packing_stats()["packed_chunks"] >= 2          # each device's host thread packed its own range
+    # flat outputs: every device fills its own share of the pools, offsets are absolute
+    flat = h2.analyze_flat(ev["signal"], ev["pres"], ev["corr_time_HMS"])
+    assert flat["n_pulses"] == int(one["wfnpulse"].sum())
+    for e in (0, E // 2 - 1, E // 2, E - 1):
+        ft, fa, _ = pkg.flatten_event(one["wfnpulse"][e], one["wftime"][e], one["wfampl"][e])
+        o, n = int(flat["pulse_offset"][e]), int(flat["pulse_count"][e])
+        assert n == len(ft) and np.array_equal(flat["wftime_pool"][o:o + n], ft) and np.array_equal(flat["wfampl_pool"][o:o + n], fa)
+    assert flat["pulse_offset"][E // 2] >= flat["wftime_pool"].size // 2       # the second device's share starts at the middle
 
 
 def test_host_packing_is_lossless_and_falls_back(pkg, calib, events):
