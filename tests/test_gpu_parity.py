@@ -499,11 +499,27 @@ def test_host_packing_is_lossless_and_falls_back(pkg, calib, events):
         assert after["raw_chunks"] == before["raw_chunks"] + 1 and after["packed_chunks"] == before["packed_chunks"], bad
         for k in a:
             assert np.array_equal(a[k], b[k]), (bad, k)
+    # the one bit pattern the transport does not preserve is the sign of a zero sample.  Adversarial set: rectified
+    # traces (their minimum IS a zero sample, so minsignal, the matched-filter differences and the 3x3 sums all see
+    # zeros of either sign), signs of the zeros drawn at random -- every output must still be bit-identical
+    rng = np.random.default_rng(11)
+    s4 = np.abs(sig)
+    z = s4 == 0
+    s4[z] = np.where(rng.random(int(z.sum())) < 0.5, -0.0, 0.0)
+    assert np.signbit(s4[z]).any() and (~np.signbit(s4[z])).any() and (s4.min(axis=-1) == 0).mean() > 0.5
+    h.set_host_packing(0)
+    a = h.analyze(s4, pres, corr)
+    h.set_host_packing(2)
+    b = h.analyze(s4, pres, corr)
+    assert (a["wfnpulse"] > 0).mean() > 0.3
+    for k in a:
+        assert np.array_equal(a[k], b[k]) and np.array_equal(np.signbit(a[k]), np.signbit(b[k])), k
     # another lattice: counts * 0.5 mV
     h.set_host_packing(2, lsb_mV=0.5)
     s3 = np.round(sig * 2.0) / 2.0
+    before = h.host_packing_stats()
     c = h.analyze(s3, pres, corr)
-    assert h.host_packing_stats()["packed_chunks"] == after["packed_chunks"] + 1
+    assert h.host_packing_stats()["packed_chunks"] == before["packed_chunks"] + 1
     h.set_host_packing(0)
     d = h.analyze(s3, pres, corr)
     for k in c:
