@@ -68,7 +68,7 @@ struct DevSlot {
     int sm_count = 148;
     DevCalib cal{};
     std::vector<void *> owned;
-    Workspace ws[2];
+    Workspace ws[3];   // [0], [1]: both paths; [2]: third stage of the host pipeline (allocated with the host staging buffers)
     DeviceCounters *ctr = nullptr;
     const double *gold1 = nullptr;  // [2][138] first-iteration Gold denominators and reciprocals
     cudaStream_t own_stream = nullptr, copy_in = nullptr, copy_out = nullptr;
@@ -218,9 +218,13 @@ int alloc_workspace(npswf_handle *h, DevSlot &s, Workspace &w, int64_t cap, bool
 // Lazily allocate the staging buffers used by the host-buffer entry points.
 int ensure_io(npswf_handle *h, DevSlot &s)
 {
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 3; i++) {
         Workspace &w = s.ws[i];
         if (w.io) continue;
+        if (!w.stream) {   // the third workspace exists only for the host pipeline
+            int rc0 = alloc_workspace(h, s, w, h->chunk, false);
+            if (rc0) return rc0;
+        }
         const size_t nb = (size_t)w.cap * B;
         int rc = 0;
         if ((rc = dev_alloc(h, s, &w.signal, nb * T))) return rc;
@@ -508,8 +512,7 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
     int rc = ensure_io(h, s);
     if (rc) return rc;
     // Host buffers: a three-stage pipeline over the two workspaces -- uploads on their own stream, every kernel on
-    // one compute stream (measured: with the chunks' kernels on two streams, as in the device path, they interleave, every
-    // chunk finishes later and its download and the next upload with it: 61.8 instead of 54.2 ms per 4 736 events), downloads on a
+    // the chunk's own stream, downloads on a
     // third stream -- so the copy engines of both directions run under the kernels of the neighbouring chunks.
     // Eight to twelve chunks per call (multiples of 148 events, at least 296) keep the uncovered first upload and
     // last download short.
@@ -518,7 +521,7 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
     int64_t chunk = h->chunk;
     if (hi - lo > 2 * 296)
         chunk = std::min<int64_t>(h->chunk, std::max<int64_t>(296, ((hi - lo + target * 148 - 1) / (target * 148)) * 148));
-    cudaStream_t s_in = s.copy_in, s_out = s.copy_out, s_cmp = s.ws[0].stream;
+    cudaStream_t s_in = s.copy_in, s_out = s.copy_out;
     // binary64 host layout: events go over as int16 counts when that is lossless (host_pack.hpp).  The host threads
     // (pack_rate, measured) and the copy engine (~48 GB/s from pinned memory) feed the device side by side: in auto
     // mode the first n_raw events of every chunk are uploaded as they are while the host packs the rest, with the
@@ -563,7 +566,7 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
     if (io.flat) {
         pool_cur = (int64_t)((__int128)io.pool_cap * lo / io.n_total);
         pool_hi = (int64_t)((__int128)io.pool_cap * hi / io.n_total);
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < 3; i++) {
             Workspace &w = s.ws[i];
             if (w.flat_t) continue;
             if ((rc = dev_alloc(h, s, &w.ev_total, (size_t)w.cap))) return rc;
@@ -621,9 +624,14 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
         }
         cuts.push_back(hi);
     }
-    for (size_t ci = 0; ci + 1 < cuts.size(); ci++, which ^= 1, k++) {
+    for (size_t ci = 0; ci + 1 < cuts.size(); ci++, which = (which + 1) % 3, k++) {
         const int64_t e0 = cuts[ci];
         Workspace &w = s.ws[which];
+        // Three workspaces, each with its own stream, two chunks computing at a time: the front and search kernels of
+        // chunk k+1 fill the SMs that the fit tails of chunk k leave idle (as in the device path), while the third
+        // workspace is being downloaded / refilled -- with two workspaces the later completion of every chunk stalls
+        // the uploads (measured: 61.8 instead of 54.2 ms per 4 736 events).  Stage profiling: one stream, clean times.
+        cudaStream_t s_cmp = h->profiling ? s.ws[0].stream : w.stream;
         const int64_t n = cuts[ci + 1] - e0;
         const size_t nb = (size_t)n * B, ob = (size_t)e0 * B;
         // events [0, n_raw) of the chunk travel as doubles, [n_raw, n) as counts
@@ -641,8 +649,8 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
         }
         const int64_t n_cnt = n - n_raw;
         bool staged = false;
-        // upload: the workspace must have been drained by the download of chunk k - 2
-        if (k >= 2) CU_TRY(h, cudaStreamWaitEvent(s_in, w.ev_out, 0));
+        // upload: the workspace must have been drained by the download of chunk k - 3
+        if (k >= 3) CU_TRY(h, cudaStreamWaitEvent(s_in, w.ev_out, 0));
         if (pack) {
             // the raw part first: the copy engine works on it while the host packs the rest
             if (n_raw > 0)
@@ -695,8 +703,9 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
         if (io.corr) CU_TRY(h, cudaMemcpyAsync(w.corr, io.corr + e0, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s_in));
         else CU_TRY(h, cudaMemsetAsync(w.corr, 0, (size_t)n * sizeof(double), s_in));
         CU_TRY(h, cudaEventRecord(w.ev_in, s_in));
-        // compute
+        // compute: after the upload, and not before chunk k - 2 is done (two chunks in flight)
         CU_TRY(h, cudaStreamWaitEvent(s_cmp, w.ev_in, 0));
+        if (k >= 2) CU_TRY(h, cudaStreamWaitEvent(s_cmp, s.ws[(which + 1) % 3].ev_cmp, 0));
         if (io.packed) {
             unpack_kernel<<<(unsigned)std::min<int64_t>(n, 4 * s.sm_count), UNPACK_THREADS, 0, s_cmp>>>(
                 w.packed, w.poffs, (long long)io.offsets[e0], n, w.signal, w.pres);
@@ -744,7 +753,7 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
     if ((rc = finish_flat())) return rc;
     if (io.flat && io.pulses_out) io.pulses_out[d] = pool_cur - (int64_t)((__int128)io.pool_cap * lo / io.n_total);
     CU_TRY(h, cudaStreamSynchronize(s_in));
-    CU_TRY(h, cudaStreamSynchronize(s_cmp));
+    for (int i = 0; i < 3; i++) CU_TRY(h, cudaStreamSynchronize(s.ws[i].stream));
     CU_TRY(h, cudaStreamSynchronize(s_out));
     return fold_profile(h, s);
 }
@@ -1042,12 +1051,12 @@ void npswf_destroy(npswf_handle *h)
     for (DevSlot &s : h->slots) {
         cudaSetDevice(s.device);
         cudaDeviceSynchronize();
-        for (int i = 0; i < 2; i++)
+        for (int i = 0; i < 3; i++)
             if (s.ws[i].stream) cudaStreamDestroy(s.ws[i].stream);
         if (s.own_stream) cudaStreamDestroy(s.own_stream);
         if (s.copy_in) cudaStreamDestroy(s.copy_in);
         if (s.copy_out) cudaStreamDestroy(s.copy_out);
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < 3; i++) {
             if (s.ws[i].ev_in) cudaEventDestroy(s.ws[i].ev_in);
             if (s.ws[i].ev_cmp) cudaEventDestroy(s.ws[i].ev_cmp);
             if (s.ws[i].ev_out) cudaEventDestroy(s.ws[i].ev_out);
