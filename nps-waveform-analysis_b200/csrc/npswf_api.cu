@@ -562,7 +562,8 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
     // flat outputs: this range owns the slice [pool_lo, pool_hi) of the caller's pulse pools; the copy of a chunk's
     // pulses is enqueued one iteration later, when its pulse count has reached the host (no bubble in the pipeline)
     int64_t pool_cur = 0, pool_hi = 0;
-    struct Pending { Workspace *w; int64_t e0, n; } pend{nullptr, 0, 0};
+    struct Pending { Workspace *w; int64_t e0, n; };
+    Pending pend{nullptr, 0, 0}, pend2{nullptr, 0, 0};   // the two chunks whose pulse copies are not enqueued yet (older first)
     if (io.flat) {
         pool_cur = (int64_t)((__int128)io.pool_cap * lo / io.n_total);
         pool_hi = (int64_t)((__int128)io.pool_cap * hi / io.n_total);
@@ -589,6 +590,7 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
             h->err = b;
             cudaDeviceSynchronize();   // leave nothing in flight that still reads or writes the caller's buffers
             pend.w = nullptr;
+            pend2.w = nullptr;
             return NPSWF_ERR_NOMEM;
         }
         if (total > 0) {
@@ -601,7 +603,8 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
         }
         pool_cur += total;
         CU_TRY(h, cudaEventRecord(pw.ev_out, s_out));
-        pend.w = nullptr;
+        pend = pend2;
+        pend2.w = nullptr;
         return 0;
     };
     int which = 0;
@@ -731,8 +734,9 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
             CU_TRY(h, cudaGetLastError());
         }
         CU_TRY(h, cudaEventRecord(w.ev_cmp, s_cmp));
-        // the pulses of the previous chunk go first on the download stream (its workspace is the next to be refilled)
-        if ((rc = finish_flat())) return rc;
+        // the pulses of chunk k - 2 go first on the download stream: its workspace is the next to be refilled, and its
+        // pulse count has long reached the host (waiting for chunk k - 1 here would stop the host from running ahead)
+        if (pend2.w && (rc = finish_flat())) return rc;
         // download
         CU_TRY(h, cudaStreamWaitEvent(s_out, w.ev_cmp, 0));
         if (io.wfnpulse) CU_TRY(h, cudaMemcpyAsync(io.wfnpulse + ob, w.wfnpulse, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s_out));
@@ -745,12 +749,13 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
         if (io.flat) {
             CU_TRY(h, cudaMemcpyAsync(w.h_ev_off, w.ev_off, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost, s_out));
             CU_TRY(h, cudaEventRecord(w.ev_tot, s_out));
-            pend = Pending{&w, e0, n};   // ev_out is recorded by finish_flat()
+            (pend.w ? pend2 : pend) = Pending{&w, e0, n};   // ev_out is recorded by finish_flat()
         } else {
             CU_TRY(h, cudaEventRecord(w.ev_out, s_out));
         }
     }
-    if ((rc = finish_flat())) return rc;
+    while (pend.w)
+        if ((rc = finish_flat())) return rc;
     if (io.flat && io.pulses_out) io.pulses_out[d] = pool_cur - (int64_t)((__int128)io.pool_cap * lo / io.n_total);
     CU_TRY(h, cudaStreamSynchronize(s_in));
     for (int i = 0; i < 3; i++) CU_TRY(h, cudaStreamSynchronize(s.ws[i].stream));
