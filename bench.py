@@ -141,7 +141,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch-events", type=int, default=2368, help="events per step per GPU (multiple of 592)")
+    ap.add_argument("--batch-events", type=int, default=9472,
+                    help="events per step per GPU: one npswf_analyze_batch_device call, which the library cuts into two chunks of 4 736")
     ap.add_argument("--e2e-events", type=int, default=4736, help="events per end-to-end step per GPU")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--stage-steps", type=int, default=4, help="steps of the serialised stage-profiling pass")
@@ -466,7 +467,8 @@ def main():
                    "fit_iterations_mean": iters / max(1, fitted), "fallback": n_fb, "retry_ok": n_retry,
                    "l2": "inputs larger than L2: %.2f GB of traces per step, two resident batches alternated" % (E * NB * NT * 8 / 1e9)},
         "clocks": clocks, "e2e": e2e,
-        "gpu_launches": int(args.steps * ((E + h.chunk_events - 1) // h.chunk_events) * 21),  # front, search, compact, 18 fit kernels per chunk
+        # front, search, compact and 18 fit kernels per chunk; chunks per step as counted by the library in the stage pass
+        "gpu_launches": int(args.steps * (chunks // max(1, args.stage_steps)) * 21),
         "roofline": roofline, "stages": stage_rows,
         "fit_fp64": {"gflops": fit_gflops, "flops_per_iter_model": flops_iter, "fp64_peak_gflops_measured": fp64_peak,
                      "frac_of_fp64_peak": fit_gflops / fp64_peak if fp64_peak > 0 else None,

@@ -32,7 +32,8 @@ namespace {
 std::string g_create_error;
 
 struct Workspace {  // per (device, pipeline stage) buffers for up to `cap` events
-    int64_t cap = 0;
+    int64_t cap = 0;       // events the scratch buffers and job lists hold
+    int64_t io_cap = 0;    // events the host-path staging buffers (signal ... status) hold: the host-path chunk limit
     double *signal = nullptr;
     int16_t *counts = nullptr;
     double *packed = nullptr;       // packed hcana stream of a chunk (npswf_analyze_batch_packed)
@@ -103,7 +104,11 @@ struct npswf_handle {
     std::vector<double> mfyref, mfint, spline, timeref;
     std::string err;
     NpsWfCounters host_ctr{};
-    int64_t chunk = 1184;  // events per chunk (8 x 148 SMs): large enough to amortise the fit kernels' tails
+    int64_t chunk = 1184;  // host path: largest chunk (8 x 148 SMs); the pipeline wants 8-12 chunks per call
+    int64_t dev_cap = 4736; // device path: largest chunk.  A call is cut into two chunks (>= 1184 events each) up to this size:
+                            // the fit kernels' tails cost the same for a short and a long job list (fit stage per 2 368 events:
+                            // 8.97 ms in chunks of 1 184, 7.76 in 2 368, 7.03 in 4 736)
+    bool chunk_fixed = false;   // cfg.chunk_events given: every path uses exactly that chunk size
     std::mutex mu;
     bool profiling = false;
     int pack_mode = 1;                 // 0 off, 1 auto (on while it is faster than the raw upload), 2 always
@@ -225,11 +230,12 @@ int ensure_io(npswf_handle *h, DevSlot &s)
             int rc0 = alloc_workspace(h, s, w, h->chunk, false);
             if (rc0) return rc0;
         }
-        const size_t nb = (size_t)w.cap * B;
+        w.io_cap = std::min<int64_t>(w.cap, h->chunk);
+        const size_t nb = (size_t)w.io_cap * B;
         int rc = 0;
         if ((rc = dev_alloc(h, s, &w.signal, nb * T))) return rc;
         if ((rc = dev_alloc(h, s, &w.pres, nb))) return rc;
-        if ((rc = dev_alloc(h, s, &w.corr, (size_t)w.cap))) return rc;
+        if ((rc = dev_alloc(h, s, &w.corr, (size_t)w.io_cap))) return rc;
         if ((rc = dev_alloc(h, s, &w.wfnpulse, nb))) return rc;
         if ((rc = dev_alloc(h, s, &w.wftime, nb * MAXP))) return rc;
         if ((rc = dev_alloc(h, s, &w.wfampl, nb * MAXP))) return rc;
@@ -572,8 +578,8 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
             if (w.flat_t) continue;
             if ((rc = dev_alloc(h, s, &w.ev_total, (size_t)w.cap))) return rc;
             if ((rc = dev_alloc(h, s, &w.ev_off, (size_t)w.cap + 1))) return rc;
-            if ((rc = dev_alloc(h, s, &w.flat_t, (size_t)w.cap * B * MAXP))) return rc;
-            if ((rc = dev_alloc(h, s, &w.flat_a, (size_t)w.cap * B * MAXP))) return rc;
+            if ((rc = dev_alloc(h, s, &w.flat_t, (size_t)w.io_cap * B * MAXP))) return rc;
+            if ((rc = dev_alloc(h, s, &w.flat_a, (size_t)w.io_cap * B * MAXP))) return rc;
             CU_TRY(h, cudaHostAlloc((void **)&w.h_ev_off, ((size_t)w.cap + 1) * sizeof(int), cudaHostAllocPortable));
             CU_TRY(h, cudaEventCreateWithFlags(&w.ev_tot, cudaEventDisableTiming));
         }
@@ -672,7 +678,7 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
                     s.pack_bytes += (double)cnt * sizeof(double);
                     if (dt > 0) s.pack_rate = 0.5 * s.pack_rate + 0.5 * (double)cnt * sizeof(double) / dt;
                     if (!w.counts) {
-                        if ((rc = dev_alloc(h, s, &w.counts, (size_t)w.cap * B * T))) return rc;
+                        if ((rc = dev_alloc(h, s, &w.counts, (size_t)w.io_cap * B * T))) return rc;
                     }
                     CU_TRY(h, cudaMemcpyAsync(w.counts, s.stage[sb], cnt * sizeof(int16_t), cudaMemcpyHostToDevice, s_in));
                     CU_TRY(h, cudaEventRecord(s.stage_ev[sb], s_in));
@@ -696,7 +702,7 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
             CU_TRY(h, cudaMemcpyAsync(w.poffs, io.offsets + e0, (size_t)(n + 1) * sizeof(long long), cudaMemcpyHostToDevice, s_in));
         } else if (io.counts) {
             if (!w.counts) {
-                if ((rc = dev_alloc(h, s, &w.counts, (size_t)w.cap * B * T))) return rc;
+                if ((rc = dev_alloc(h, s, &w.counts, (size_t)w.io_cap * B * T))) return rc;
             }
             CU_TRY(h, cudaMemcpyAsync(w.counts, io.counts + ob * T, nb * T * sizeof(int16_t), cudaMemcpyHostToDevice, s_in));
         } else {
@@ -828,6 +834,8 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
     h->kp.fit_retry_max_iter = cfg->fit_retry_max_iter > 0 ? cfg->fit_retry_max_iter : 100;
     h->kp.fit_thread_tries = (getenv("NPSWF_FIT_THREAD_TRIES") && atoi(getenv("NPSWF_FIT_THREAD_TRIES")) > 0) ? atoi(getenv("NPSWF_FIT_THREAD_TRIES")) : 20;
     h->chunk = cfg->chunk_events > 0 ? cfg->chunk_events : 1184;
+    h->chunk_fixed = cfg->chunk_events > 0;
+    h->dev_cap = h->chunk_fixed ? h->chunk : 4736;
     {
         // host threads for the lossless int16 transport: the cores of this process's share of the node, at most 16
         const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
@@ -1001,7 +1009,7 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
             CR(cudaEventCreateWithFlags(&s.fit_join[i], cudaEventDisableTiming));
         }
         for (int i = 0; i < 2; i++)
-            if ((rc = alloc_workspace(h, s, s.ws[i], h->chunk, false))) return fail(rc);
+            if ((rc = alloc_workspace(h, s, s.ws[i], h->dev_cap, false))) return fail(rc);
         CR(cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRONT_SMEM));
         CR(cudaFuncSetAttribute(search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEARCH_SMEM));
         CR(cudaFuncSetAttribute(fit_kernel<25>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1337,15 +1345,17 @@ int npswf_analyze_batch_device(npswf_handle *h, int32_t dev_slot, int64_t n_even
     // Chunks alternate between the two workspaces, each on its own internal stream forked from / joined to the
     // caller's stream: the front + search kernels of chunk k+1 fill the SMs the fit tails of chunk k leave idle.
     // With stage profiling on everything is serialised on the caller's stream so that the stage times are clean.
-    const bool overlap = !h->profiling && n_events > s.ws[0].cap;
+    int64_t chunk = s.ws[0].cap;
+    if (!h->chunk_fixed) chunk = std::min<int64_t>(chunk, std::max<int64_t>(1184, ((n_events + 1) / 2 + 147) / 148 * 148));
+    const bool overlap = !h->profiling && n_events > chunk;
     if (overlap) {
         CU_TRY(h, cudaEventRecord(s.fit_fork, st));
         for (int i = 0; i < 2; i++) CU_TRY(h, cudaStreamWaitEvent(s.ws[i].stream, s.fit_fork, 0));
     }
     int which = 0;
-    for (int64_t e0 = 0; e0 < n_events; e0 += s.ws[0].cap, which ^= 1) {
+    for (int64_t e0 = 0; e0 < n_events; e0 += chunk, which ^= 1) {
         Workspace &w = s.ws[overlap ? which : 0];
-        const int64_t n = std::min<int64_t>(w.cap, n_events - e0);
+        const int64_t n = std::min<int64_t>(chunk, n_events - e0);
         const size_t ob = (size_t)e0 * B;
         rc = run_chunk(h, s, w, overlap ? w.stream : st, n, d_signal + ob * T, d_pres + ob, d_corr ? d_corr + e0 : nullptr,
                        d_wfnpulse ? d_wfnpulse + ob : nullptr, d_wftime + ob * MAXP, d_wfampl + ob * MAXP, d_chi2 + ob,
@@ -1406,8 +1416,8 @@ int npswf_find_pulses_mf_batch(npswf_handle *h, int64_t n_events, const double *
     if ((rc = ensure_io(h, s))) return rc;
     Workspace &w = s.ws[0];
     cudaStream_t st = w.stream;
-    for (int64_t e0 = 0; e0 < n_events; e0 += w.cap) {
-        const int64_t n = std::min<int64_t>(w.cap, n_events - e0);
+    for (int64_t e0 = 0; e0 < n_events; e0 += w.io_cap) {
+        const int64_t n = std::min<int64_t>(w.io_cap, n_events - e0);
         const size_t nb = (size_t)n * B, ob = (size_t)e0 * B;
         CU_TRY(h, cudaMemcpyAsync(w.signal, signal + ob * T, nb * T * sizeof(double), cudaMemcpyHostToDevice, st));
         CU_TRY(h, cudaMemcpyAsync(w.pres, pres + ob, nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -1436,8 +1446,8 @@ int npswf_pass_cluster_threshold_batch(npswf_handle *h, int64_t n_events, const 
     Workspace &w = s.ws[0];
     cudaStream_t st = w.stream;
     std::vector<uint8_t> tmp;
-    for (int64_t e0 = 0; e0 < n_events; e0 += w.cap) {
-        const int64_t n = std::min<int64_t>(w.cap, n_events - e0);
+    for (int64_t e0 = 0; e0 < n_events; e0 += w.io_cap) {
+        const int64_t n = std::min<int64_t>(w.io_cap, n_events - e0);
         const size_t nb = (size_t)n * B, ob = (size_t)e0 * B;
         CU_TRY(h, cudaMemcpyAsync(w.signal, signal + ob * T, nb * T * sizeof(double), cudaMemcpyHostToDevice, st));
         CU_TRY(h, cudaMemcpyAsync(w.pres, pres + ob, nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -1460,8 +1470,8 @@ int npswf_matched_filter_batch(npswf_handle *h, int64_t n_events, const double *
     if ((rc = ensure_io(h, s))) return rc;
     Workspace &w = s.ws[0];
     cudaStream_t st = w.stream;
-    for (int64_t e0 = 0; e0 < n_events; e0 += w.cap) {
-        const int64_t n = std::min<int64_t>(w.cap, n_events - e0);
+    for (int64_t e0 = 0; e0 < n_events; e0 += w.io_cap) {
+        const int64_t n = std::min<int64_t>(w.io_cap, n_events - e0);
         const size_t nb = (size_t)n * B, ob = (size_t)e0 * B;
         CU_TRY(h, cudaMemcpyAsync(w.signal, signal + ob * T, nb * T * sizeof(double), cudaMemcpyHostToDevice, st));
         CU_TRY(h, cudaMemcpyAsync(w.pres, pres + ob, nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -1486,8 +1496,8 @@ int npswf_fitwf_batch(npswf_handle *h, int64_t n_events, const double *signal, c
     if ((rc = ensure_io(h, s))) return rc;
     Workspace &w = s.ws[0];
     cudaStream_t st = w.stream;
-    for (int64_t e0 = 0; e0 < n_events; e0 += w.cap) {
-        const int64_t n = std::min<int64_t>(w.cap, n_events - e0);
+    for (int64_t e0 = 0; e0 < n_events; e0 += w.io_cap) {
+        const int64_t n = std::min<int64_t>(w.io_cap, n_events - e0);
         const size_t nb = (size_t)n * B, ob = (size_t)e0 * B;
         CU_TRY(h, cudaMemcpyAsync(w.signal, signal + ob * T, nb * T * sizeof(double), cudaMemcpyHostToDevice, st));
         if (corr_time_HMS) CU_TRY(h, cudaMemcpyAsync(w.corr, corr_time_HMS + e0, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
