@@ -185,6 +185,49 @@ int dev_upload(npswf_handle *h, DevSlot &s, const Tp **dst, const Tp *src, size_
     return 0;
 }
 
+template <class Tp>
+void dev_free(DevSlot &s, Tp **p)
+{
+    if (!*p) return;
+    for (size_t i = 0; i < s.owned.size(); i++)
+        if (s.owned[i] == (void *)*p) { s.owned.erase(s.owned.begin() + (long)i); break; }
+    cudaFree((void *)*p);
+    *p = nullptr;
+}
+
+// scratch buffers and job lists of a workspace for `cap` events
+int alloc_scratch(npswf_handle *h, DevSlot &s, Workspace &w, int64_t cap)
+{
+    w.cap = cap;
+    const size_t nb = (size_t)cap * B;
+    int rc = 0;
+    if ((rc = dev_alloc(h, s, &w.mf, nb * T))) return rc;
+    if ((rc = dev_alloc(h, s, &w.minsig, nb))) return rc;
+    if ((rc = dev_alloc(h, s, &w.flags, nb))) return rc;
+    if ((rc = dev_alloc(h, s, &w.cont_list, (size_t)6 * nb))) return rc;
+    if ((rc = dev_alloc(h, s, &w.cont_state, (size_t)3 * nb * FT_CONT_STRIDE))) return rc;
+    if ((rc = dev_alloc(h, s, &w.fit_list, (size_t)(MAXP + 1) * nb))) return rc;
+    if ((rc = dev_alloc(h, s, &w.fit_dense, (size_t)(MAXP + 1) * nb))) return rc;
+    return 0;
+}
+
+// The device path cuts a call into two chunks of up to dev_cap events: the scratch of both workspaces grows to the
+// chunk size a call needs the first time it is needed (device idle), so a handle that only sees small calls stays small.
+int grow_scratch(npswf_handle *h, DevSlot &s, int64_t cap)
+{
+    if (s.ws[0].cap >= cap && s.ws[1].cap >= cap) return 0;
+    CU_TRY(h, cudaDeviceSynchronize());
+    for (int i = 0; i < 2; i++) {
+        Workspace &w = s.ws[i];
+        if (w.cap >= cap) continue;
+        dev_free(s, &w.mf); dev_free(s, &w.minsig); dev_free(s, &w.flags); dev_free(s, &w.cont_list);
+        dev_free(s, &w.cont_state); dev_free(s, &w.fit_list); dev_free(s, &w.fit_dense);
+        int rc = alloc_scratch(h, s, w, cap);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 int alloc_workspace(npswf_handle *h, DevSlot &s, Workspace &w, int64_t cap, bool io)
 {
     w.cap = cap;
@@ -204,15 +247,9 @@ int alloc_workspace(npswf_handle *h, DevSlot &s, Workspace &w, int64_t cap, bool
         if ((rc = dev_alloc(h, s, &w.status, nb))) return rc;
         if ((rc = dev_alloc(h, s, &w.mask, nb))) return rc;
     }
-    if ((rc = dev_alloc(h, s, &w.mf, nb * T))) return rc;
-    if ((rc = dev_alloc(h, s, &w.minsig, nb))) return rc;
-    if ((rc = dev_alloc(h, s, &w.flags, nb))) return rc;
+    if ((rc = alloc_scratch(h, s, w, cap))) return rc;
     if ((rc = dev_alloc(h, s, &w.fit_count, 64))) return rc;
-    if ((rc = dev_alloc(h, s, &w.cont_list, (size_t)6 * nb))) return rc;
-    if ((rc = dev_alloc(h, s, &w.cont_state, (size_t)3 * nb * FT_CONT_STRIDE))) return rc;
     if ((rc = dev_alloc(h, s, &w.bucket_count, (size_t)(MAXP + 1) * B))) return rc;
-    if ((rc = dev_alloc(h, s, &w.fit_list, (size_t)(MAXP + 1) * nb))) return rc;
-    if ((rc = dev_alloc(h, s, &w.fit_dense, (size_t)(MAXP + 1) * nb))) return rc;
     CU_TRY(h, cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
     CU_TRY(h, cudaEventCreateWithFlags(&w.ev_in, cudaEventDisableTiming));
     CU_TRY(h, cudaEventCreateWithFlags(&w.ev_cmp, cudaEventDisableTiming));
@@ -1009,7 +1046,7 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
             CR(cudaEventCreateWithFlags(&s.fit_join[i], cudaEventDisableTiming));
         }
         for (int i = 0; i < 2; i++)
-            if ((rc = alloc_workspace(h, s, s.ws[i], h->dev_cap, false))) return fail(rc);
+            if ((rc = alloc_workspace(h, s, s.ws[i], h->chunk, false))) return fail(rc);
         CR(cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRONT_SMEM));
         CR(cudaFuncSetAttribute(search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEARCH_SMEM));
         CR(cudaFuncSetAttribute(fit_kernel<25>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1345,8 +1382,11 @@ int npswf_analyze_batch_device(npswf_handle *h, int32_t dev_slot, int64_t n_even
     // Chunks alternate between the two workspaces, each on its own internal stream forked from / joined to the
     // caller's stream: the front + search kernels of chunk k+1 fill the SMs the fit tails of chunk k leave idle.
     // With stage profiling on everything is serialised on the caller's stream so that the stage times are clean.
-    int64_t chunk = s.ws[0].cap;
-    if (!h->chunk_fixed) chunk = std::min<int64_t>(chunk, std::max<int64_t>(1184, ((n_events + 1) / 2 + 147) / 148 * 148));
+    int64_t chunk = h->chunk;
+    if (!h->chunk_fixed) {
+        chunk = std::min<int64_t>(h->dev_cap, std::max<int64_t>(h->chunk, ((n_events + 1) / 2 + 147) / 148 * 148));
+        if ((rc = grow_scratch(h, s, chunk))) return rc;
+    }
     const bool overlap = !h->profiling && n_events > chunk;
     if (overlap) {
         CU_TRY(h, cudaEventRecord(s.fit_fork, st));
