@@ -78,7 +78,10 @@ void npsWF_gpu_event_loop(TTree *T, TTree *WF, const Float_t *tdcoffset, int bat
             for (int it = 0; it < nsamp; it++, ns++)
                 if (bloc < B && it < NT) sig[bloc * NT + it] = Samp[ns];
         }
-        corr[n] = adcCounter.GetSize() ? pulseTime[0] - pulseTimeRaw[0] / 16. - tdcoffset[(int)adcCounter[0]] : 0.;  // T2:903
+        int c0 = adcCounter.GetSize() ? (int)adcCounter[0] : 0;
+        if (c0 == 2000) c0 = 1080;                            // scintillator renumbering, T2:894-897
+        if (c0 == 2001) c0 = 1081;
+        corr[n] = adcCounter.GetSize() ? pulseTime[0] - pulseTimeRaw[0] / 16. - tdcoffset[c0] : 0.;  // T2:903
         evt[n] = *evnum;
         if (++n == batch_events) { flush(n); n = 0; }
     }
