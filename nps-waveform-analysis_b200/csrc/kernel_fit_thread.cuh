@@ -121,15 +121,12 @@ __device__ __forceinline__ void eval_thread(const double (&p)[2 * N + 1], const 
                 dsw[n] = ds * wkm;
                 d2w[n] = d2 * wkm;
                 J[2 + 2 * n] = s * wkm;
-                J[1 + 2 * n] = nA[n] * dsw[n];
+                J[1 + 2 * n] = dsw[n];   // without its factor -A_n: applied once to the sums after the loop
                 r = fma(nA[n], J[2 + 2 * n], r);
             }
             ne.c2 = fma(r, r, ne.c2);
 #pragma unroll
-            for (int n = 0; n < N; n++) {
-                ne.s1[n] = fma(r, dsw[n], ne.s1[n]);
-                ne.s2[n] = fma(r, d2w[n], ne.s2[n]);
-            }
+            for (int n = 0; n < N; n++) ne.s2[n] = fma(r, d2w[n], ne.s2[n]);
 #pragma unroll
             for (int a = 0; a < P; a++) {
                 ne.g[a] = fma(J[a], r, ne.g[a]);
@@ -146,8 +143,25 @@ __device__ __forceinline__ void eval_thread(const double (&p)[2 * N + 1], const 
         if (j0 + 2 * U < NFIT) load(j0 + 2 * U, ywA, kA);
         consume(j0 + U, ywB, kB);
     }
+    // the time columns were accumulated without their factor -A_n: sum r w S' is the second-order term s1 as it stands,
+    // and the gradient / normal-matrix entries get the factor(s) now
 #pragma unroll
-    for (int n = 0; n < N; n++) ne.s2[n] *= nA[n];
+    for (int n = 0; n < N; n++) {
+        ne.s1[n] = ne.g[1 + 2 * n];
+        ne.s2[n] *= nA[n];
+    }
+#pragma unroll
+    for (int a = 0; a < P; a++) {
+        const bool ta = a >= 1 && ((a - 1) & 1) == 0;
+        if (ta) ne.g[a] *= nA[(a - 1) >> 1];
+#pragma unroll
+        for (int b = 0; b <= a; b++) {
+            const bool tb = b >= 1 && ((b - 1) & 1) == 0;
+            if (ta && tb) ne.H[a * (a + 1) / 2 + b] *= nA[(a - 1) >> 1] * nA[(b - 1) >> 1];
+            else if (ta) ne.H[a * (a + 1) / 2 + b] *= nA[(a - 1) >> 1];
+            else if (tb) ne.H[a * (a + 1) / 2 + b] *= nA[(b - 1) >> 1];
+        }
+    }
 }
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
