@@ -19,7 +19,8 @@ namespace npswf {
 constexpr int FRONT_THREADS = 256;
 constexpr int FRONT_WARPS = FRONT_THREADS / 32;
 constexpr int FRONT_RING = 4;
-constexpr size_t FRONT_SMEM = (size_t)FRONT_RING * ROW_BYTES + 64 /*mbarriers*/ + 1088 /*pres bytes*/ + 16 + 1024 /*zero trace*/;
+constexpr size_t FRONT_SMEM = (size_t)FRONT_RING * ROW_BYTES + 64 /*mbarriers*/ + 1088 /*pres bytes*/ + 16 + 1024 /*zero trace*/ +
+                              2 * 3 * 32 * sizeof(int) /*neighbour offset tables of two rows*/;
 
 // flags byte written per (event, block)
 constexpr uint8_t FL_PRESENT = 1, FL_OKTOFIT = 2;
@@ -181,7 +182,15 @@ front_kernel(const double *__restrict__ signal, const int32_t *__restrict__ pres
     // so the 3x3 sums need no predicates
     double *zrow = reinterpret_cast<double *>(smem_raw + (size_t)FRONT_RING * ROW_BYTES + 64 + 1088 + 16);
     const int ZOFF = (int)(zrow - ring);
+    // nbr[row parity][dr + 1][col + 1]: ring offset (in doubles) of the trace of block (r + dr, col) if it is inside the grid
+    // and present in the data (T2:257), of the zero trace otherwise; built for row r + 1 while row r is processed
+    int *nbr = reinterpret_cast<int *>(smem_raw + (size_t)FRONT_RING * ROW_BYTES + 64 + 1088 + 16 + 1024);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    auto build_nbr = [&](int r) {   // threads 0..95
+        const int dr = tid / 32 - 1, cc = (tid & 31) - 1, nr = r + dr;
+        const bool in = (unsigned)nr < (unsigned)NLIN && (unsigned)cc < (unsigned)NCOL && (pres1[min(max(nr, 0), NLIN - 1) * NCOL + min(max(cc, 0), NCOL - 1)] & 1);
+        nbr[(r & 1) * 96 + tid] = in ? (nr % FRONT_RING) * ROW_DOUBLES + cc * T : ZOFF;
+    };
 
     if (tid == 0) {
         for (int i = 0; i < FRONT_RING; i++) mbar_init(&bars[i], 1);
@@ -205,6 +214,8 @@ front_kernel(const double *__restrict__ signal, const int32_t *__restrict__ pres
             pres1[i] = (pres[(size_t)e * B + i] == 1 && cal.preswf[i] == 1) ? 3 : (pres[(size_t)e * B + i] == 1 ? 1 : 0);
         // pres1 bit0: pres==1 (neighbour gate T2:257); bit1: also preswf==1 (block is analysed, T2:944)
         __syncthreads();
+        if (tid < 96) build_nbr(0);
+        __syncthreads();
 
         int waited = 0;  // rows whose barrier this thread has already waited on: rows < waited are visible
         for (int r = 0; r < NLIN; r++) {
@@ -219,6 +230,8 @@ front_kernel(const double *__restrict__ signal, const int32_t *__restrict__ pres
             // ring offsets (in doubles) of the rows r-1, r, r+1
             const int ro[3] = {((r + FRONT_RING - 1) % FRONT_RING) * ROW_DOUBLES, (r % FRONT_RING) * ROW_DOUBLES,
                                ((r + 1) % FRONT_RING) * ROW_DOUBLES};
+            if (tid < 96 && r + 1 < NLIN) build_nbr(r + 1);   // published by the barrier at the end of this row
+            const int *nb_r = nbr + (r & 1) * 96;
 
             if (do_mf) {
                 // 30 half-warp tasks: warp w takes block pairs {2w', 2w'+1}
@@ -248,12 +261,7 @@ front_kernel(const double *__restrict__ signal, const int32_t *__restrict__ pres
                     int off[9];
                     off[0] = ro[1] + col * T + lane;
 #pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        const int nr = r + dR[k], nc = col + dC[k];
-                        const bool in = (unsigned)nr < (unsigned)NLIN && (unsigned)nc < (unsigned)NCOL &&
-                                        (pres1[min(max(nr, 0), NLIN - 1) * NCOL + min(max(nc, 0), NCOL - 1)] & 1);
-                        off[1 + k] = (in ? ro[1 + dR[k]] + nc * T : ZOFF) + lane;
-                    }
+                    for (int k = 0; k < 8; k++) off[1 + k] = nb_r[(dR[k] + 1) * 32 + col + dC[k] + 1] + lane;
                     // window |it - center| < coinc_width (T2:267) as the integer interval [lo, lo + span], evaluated
                     // with the reference's own expression on the host (npswf_create)
                     const int wlo = cal.win_lo[bn];
@@ -270,11 +278,16 @@ front_kernel(const double *__restrict__ signal, const int32_t *__restrict__ pres
                             if ((unsigned)(it - wlo) <= wspan) wmax = dmax2(wmax, sum);
                         }
                     }
+                    // one butterfly for both: the lower half-warp reduces the minimum, the upper one the negated maximum
+                    // (negation is exact and turns max into min)
+                    const double nmax = -wmax;
+                    const bool up = lane >= 16;
+                    double keep = up ? nmax : gmin;
+                    keep = dmin2(keep, __shfl_xor_sync(0xffffffffu, up ? gmin : nmax, 16));
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        gmin = dmin2(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
-                        wmax = dmax2(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-                    }
+                    for (int o = 8; o > 0; o >>= 1) keep = dmin2(keep, __shfl_xor_sync(0xffffffffu, keep, o));
+                    gmin = __shfl_sync(0xffffffffu, keep, 0);
+                    wmax = -__shfl_sync(0xffffffffu, keep, 16);
                     ok = dsub(wmax, gmin) > kp.trig_thres;  // T2:277
                 }
                 if (lane == 0 && flags_out)
