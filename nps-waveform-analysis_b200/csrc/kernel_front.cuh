@@ -133,12 +133,14 @@ __device__ __forceinline__ void mf_block_halfwarp(const double *__restrict__ s, 
             double a = 0.0;
 #pragma unroll
             for (int jt = 0; jt < MFW; jt++) a = dadd(a, __shfl_sync(FULL, term, half + jt));
-            if (mh && hl == L) { F[o] = a; candmask |= 1u << o; emin = dmin2(emin, a); }
+            // every lane of the half-warp holds the same sum a: the minimum is tracked by all of them, no reduction
+            if (mh) {
+                emin = dmin2(emin, a);
+                if (hl == L) { F[o] = a; candmask |= 1u << o; }
+            }
             mh &= mh - 1;
         }
     }
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) emin = dmin2(emin, __shfl_xor_sync(FULL, emin, o));
     if (!active) return;
     if (hl == 0 && minsig_out) *minsig_out = mn;
     if (mf_out) {
