@@ -22,6 +22,7 @@ struct EventResult {                      // what analyze() returns per event (T
     std::vector<int32_t> wfnpulse;              // [1080]
     std::vector<double> wfampl, wftime;         // flattened: blocks with pulses only, block order
     std::vector<int32_t> blockOffset;           // [1081]
+    std::vector<double> h2time;                 // wftime of the pulses with wfampl > 20, block order (T2:990-992)
 };
 
 class Analyzer {
@@ -52,12 +53,13 @@ public:
         std::vector<int32_t> n(nb), cnt((size_t)n_events);
         std::vector<int64_t> off((size_t)n_events);
         std::vector<double> c(nb), tw(nb), aw(nb), pt, pa;
+        std::vector<uint8_t> st(nb);
         for (int64_t per_block : {4, (int)NPSWF_MAXWFPULSES}) {
             pt.resize(nb * (size_t)per_block);
             pa.resize(pt.size());
             const int rc = npswf_analyze_batch_flat(h_, n_events, signal, pres, corr_time_HMS, n.data(), off.data(), cnt.data(),
                                                     pt.data(), pa.data(), (int64_t)pt.size(), c.data(), tw.data(), aw.data(),
-                                                    nullptr, nullptr);
+                                                    st.data(), nullptr);
             if (rc == NPSWF_ERR_NOMEM && per_block < (int)NPSWF_MAXWFPULSES) continue;
             check(rc);
             break;
@@ -79,6 +81,14 @@ public:
             r.blockOffset[NPSWF_NBLOCKS] = run;          // T2:1022
             r.wftime.assign(pt.begin() + off[e], pt.begin() + off[e] + cnt[e]);
             r.wfampl.assign(pa.begin() + off[e], pa.begin() + off[e] + cnt[e]);
+            // T2:987-996 runs for the blocks that were fitted (the others `continue` at T2:984): status bit okToFit
+            // is not returned here, chi2/wfnpulse tell the same -- a block with pulses that was not fitted keeps
+            // its times in bins and chi2 = -100 with no fall-back conversion; the reference skips it too
+            // (h1time needs Minuit's parameter objects and is not reproduced)
+            for (int b = 0; b < NPSWF_NBLOCKS; b++)
+                for (int p = 0; p < r.wfnpulse[b]; p++)
+                    if (st[o + b] & NPSWF_ST_OKTOFIT)
+                        if (r.wfampl[(size_t)r.blockOffset[b] + p] > 20) r.h2time.push_back(r.wftime[(size_t)r.blockOffset[b] + p]);
         }
         return out;
     }

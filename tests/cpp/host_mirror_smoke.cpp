@@ -68,6 +68,13 @@ int main()
                 if (r.blockOffset[b] != bo[b]) return 7;
             for (int b = 0; b < B; b++)
                 if (r.wfnpulse[b] != n[o + b] || r.chi2[b] != c[o + b] || r.timewf[b] != tw[o + b] || r.amplwf[b] != aw[o + b]) return 8;
+            // h2time: times of the fitted blocks' pulses with amplitude > 20 (T2:987-992)
+            std::vector<double> h2;
+            for (int b = 0; b < B; b++)
+                if (st[o + b] & NPSWF_ST_OKTOFIT)
+                    for (int p = 0; p < n[o + b]; p++)
+                        if (a[(o + b) * NPSWF_MAXWFPULSES + p] > 20) h2.push_back(t[(o + b) * NPSWF_MAXWFPULSES + p]);
+            if (h2 != r.h2time || h2.empty()) return 10;
             pulses += tot;
         }
         std::printf("gpu present: mirror analyze() == C entry point + flatten on %d events, %lld pulses\n", E, pulses);
