@@ -46,19 +46,19 @@ void npsWF_gpu_event_loop(TTree *T, TTree *WF, const Float_t *tdcoffset, int bat
 
     std::vector<double> signal((size_t)batch_events * B * NT), corr(batch_events), evt(batch_events);
     std::vector<int32_t> pres((size_t)batch_events * B);
-    std::vector<double> chi2, timewf, amplwf, wfampl, wftime;
+    std::vector<double> chi2, timewf, amplwf, wfampl, wftime, h2time;
     std::vector<Int_t> wfnpulse;
     Double_t evtOut, corrOut;
     WF->Branch("chi2", &chi2); WF->Branch("amplwf", &amplwf); WF->Branch("timewf", &timewf);
     WF->Branch("wfnpulse", &wfnpulse); WF->Branch("wfampl", &wfampl); WF->Branch("wftime", &wftime);
-    WF->Branch("evt", &evtOut); WF->Branch("corr_time_HMS", &corrOut);
+    WF->Branch("evt", &evtOut); WF->Branch("corr_time_HMS", &corrOut); WF->Branch("h2time", &h2time);
 
     auto flush = [&](int n) {
         auto res = gpu.analyze(n, signal.data(), pres.data(), corr.data());
         for (int e = 0; e < n; e++) {
             chi2 = res[e].chi2; timewf = res[e].timewf; amplwf = res[e].amplwf;
             wfnpulse.assign(res[e].wfnpulse.begin(), res[e].wfnpulse.end());
-            wfampl = res[e].wfampl; wftime = res[e].wftime;
+            wfampl = res[e].wfampl; wftime = res[e].wftime; h2time = res[e].h2time;
             evtOut = evt[e]; corrOut = corr[e];
             WF->Fill();
         }
