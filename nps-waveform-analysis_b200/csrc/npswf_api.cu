@@ -92,6 +92,7 @@ struct DevSlot {
     double pack_seconds = 0, pack_bytes = 0;
     double pack_rate = 0;                                    // running estimate, bytes of doubles per second
     bool pack_unavailable = false;                           // the pinned staging buffers could not be allocated
+    unsigned pack_probe = 0;                                 // chunks sent raw because the packer is slow
 };
 
 }  // namespace
@@ -688,6 +689,10 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
                 const double a = 48.0e9 / s.pack_rate;
                 f = std::min(1.0, std::max(0.0, (a - 0.25) / (a + 0.75)));
                 if (f > 0.9) f = 1.0;
+                // a packer that slow is short of cores or of memory bandwidth (several ranks on one host): its reads
+                // would also slow the copy engine down (4 ranks: 1.51e8 packed 24 % at 18 GB/s, 1.70e8 raw), so the
+                // chunk goes over raw; a tenth of every 32nd chunk is packed to see whether that has changed
+                if (s.pack_rate < 30.0e9) f = ((++s.pack_probe & 31) == 0) ? 0.9 : 1.0;
             } else if (h->pack_mode == 1 && s.pack_rate < 10.0e9) {
                 f = 1.0;   // pageable source and one or two slow host threads: the driver's staged upload is no slower
             }
