@@ -16,11 +16,14 @@ for r in range((E + 295) // 296):
     hp[296 * r:296 * r + n] = base["pres"][:n]; hc[296 * r:296 * r + n] = base["corr_time_HMS"][:n]
 h = pkg.NpsWf(cal)
 ho = h.alloc_outputs(E, pinned=True)
-for name, mode, fn in (("f64 auto", 1, lambda: h.analyze(hs, hp, hc, out=ho)), ("f64 raw", 0, lambda: h.analyze(hs, hp, hc, out=ho)),
-                       ("i16", 0, lambda: h.analyze_i16(hk, synth.LSB, hp, hc, out=ho))):
+variants = (("f64 auto", 1, lambda: h.analyze(hs, hp, hc, out=ho)), ("f64 raw", 0, lambda: h.analyze(hs, hp, hc, out=ho)),
+                       ("i16", 0, lambda: h.analyze_i16(hk, synth.LSB, hp, hc, out=ho)))
+if os.environ.get("E2E_ONLY_AUTO"):
+    variants = variants[:1]
+for name, mode, fn in variants:
     h.set_host_packing(mode)
     fn(); fn()
     ts = []
-    for _ in range(5):
+    for _ in range(9 if os.environ.get("E2E_ONLY_AUTO") else 5):
         t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
-    print("ramp=%s %-9s best %.1f ms median %.1f ms -> %.1f M/s" % (os.environ.get("NPSWF_CHUNK_RAMP", "1"), name, min(ts) * 1e3, sorted(ts)[2] * 1e3, E * 1080 / sorted(ts)[2] / 1e6), h.host_packing_stats(), flush=True)
+    print(os.environ.get("NPSWF_LIB", "default").split("/")[-1], "ramp=%s %-9s best %.1f ms median %.1f ms -> %.1f M/s" % (os.environ.get("NPSWF_CHUNK_RAMP", "1"), name, min(ts) * 1e3, sorted(ts)[len(ts) // 2] * 1e3, E * 1080 / sorted(ts)[len(ts) // 2] / 1e6), h.host_packing_stats(), flush=True)
