@@ -400,14 +400,14 @@ def main():
     dom = max(("front", "search", "fit"), key=lambda k: stages[k + "_ms"])
     launches_per_chunk = {"front": 1, "search": 1, "fit": 14}
     # dram__bytes_read.sum + dram__bytes_write.sum per block-waveform, from the `ncu --set full` capture of this build
-    # (profiles/r1_ncu_full_final2.csv: launches of 1 184 events = 1 278 720 block-waveforms)
-    ncu_traffic_per_unit = {"front": (1.132321e9 + 539.52e6) / 1278720.0, "search": (1.798595e9 + 291.739e6) / 1278720.0}
+    # (profiles/r1_ncu_full_final6.csv: launches of 1 184 events = 1 278 720 block-waveforms)
+    ncu_traffic_per_unit = {"front": (1.133616e9 + 538.668e6) / 1278720.0, "search": (1.799080e9 + 291.132e6) / 1278720.0}
     units_per_launch = units_local / chunks
     traffic = ncu_traffic_per_unit[dom] * units_per_launch if dom in ncu_traffic_per_unit else None
     roofline = {"kernel": {"front": "front_kernel", "search": "search_kernel", "fit": "fit_thread_kernel<1,2> + fit_small_kernel + fit_kernel<25> (14 launches)"}[dom],
                 "bound": "hbm", "achieved": stage_rows[dom]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
                 "frac": stage_rows[dom]["achieved_gbs"] / hbm, "traffic": traffic,
-                "traffic_source": "ncu --set full, profiles/r1_ncu_full_final2.csv (bytes per block-waveform x block-waveforms per launch)",
+                "traffic_source": "ncu --set full, profiles/r1_ncu_full_final6.csv (bytes per block-waveform x block-waveforms per launch)",
                 "peak_source": peak_src,
                 "note": "dominant stage is FP64-pipe bound, not HBM bound (bit-faithful FP64 TSpectrum / FP64 LM); "
                         "see stages, fp64_peak_gflops_measured and DESIGN.md",
