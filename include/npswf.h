@@ -58,7 +58,20 @@ typedef struct NpsWfConfig {
     int32_t chunk_events;   /* events per internal device chunk; 0 = default (512)        */
     int32_t fit_max_iter;   /* LM iterations of the first attempt; 0 = default            */
     int32_t fit_retry_max_iter; /* LM iterations of the retry; 0 = default                */
+    int32_t fit_mode;       /* NPSWF_FIT_FAST (0, default) or NPSWF_FIT_MIGRAD: minimiser of Fitwf, see below */
+    double fit_arb_chi2;    /* FAST mode: fits ending with chi2/ndf above this are redone by the Migrad kernel from
+                               their seeds (0 = library default, < 0 = never)                                  */
 } NpsWfConfig;
+
+/* Minimiser of Fitwf (T2:693-773).
+ * NPSWF_FIT_MIGRAD: the reference's own -- Minuit2 Migrad on numerical gradients, strategy 1, retry with strategy 2
+ *   from the same seeds, EDM goal 2e-5, call limit 1000+100P+5P^2 -- re-implemented for the device
+ *   (csrc/migrad_core.hpp, fit_migrad_kernel) in the reference's FMA-free arithmetic and summation order: fitted
+ *   values, chi2 and the ok / retry / fall-back verdict follow Migrad's path.
+ * NPSWF_FIT_FAST: Levenberg-Marquardt on analytic spline derivatives (fit_thread_kernel & co.), ~10x cheaper; it
+ *   converges the same chi2 tighter than Migrad's EDM goal, and where the chi2 has several local minima it may end
+ *   in another one than Migrad does. */
+enum { NPSWF_FIT_FAST = 0, NPSWF_FIT_MIGRAD = 1 };
 
 /* The calibration globals of T2:74-85 as loaded at T2:360-469.  mfyref / mfint are derived
  * inside npswf_create exactly as T2:440-451 does. */

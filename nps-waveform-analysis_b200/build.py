@@ -26,9 +26,24 @@ def build(force=False, verbose=False):
     out = os.path.join(HERE, "lib", "libnpswf.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     if force or _stale(out, srcs):
-        cmd = [NVCC] + ARCH + COMMON + (["-Xptxas", "-v"] if verbose else []) + \
-              ["-o", out, os.path.join(csrc, "npswf_api.cu"), os.path.join(csrc, "host_pack.cpp")]
-        subprocess.check_call(cmd)
+        # two device translation units: npswf_api.cu (default FMA contraction; its bit-exact parts use explicit
+        # __dmul_rn / __dadd_rn) and npswf_migrad.cu, whose whole arithmetic follows an FMA-free x86-64 build of
+        # Minuit2 (-fmad=false).  Compiled side by side, then linked with the host packer.
+        obj = os.path.join(HERE, "lib", "obj")
+        os.makedirs(obj, exist_ok=True)
+        vflag = ["-Xptxas", "-v"] if verbose else []
+        units = [("npswf_api.cu", []), ("npswf_migrad.cu", ["-fmad=false"]), ("host_pack.cpp", [])]
+        procs = []
+        for name, extra in units:
+            o = os.path.join(obj, os.path.splitext(name)[0] + ".o")
+            if force or _stale(o, srcs):
+                cmd = [NVCC] + ARCH + [f for f in COMMON if f != "-shared"] + vflag + extra + ["-c", "-o", o, os.path.join(csrc, name)]
+                procs.append((cmd, subprocess.Popen(cmd)))
+        for cmd, pr in procs:
+            if pr.wait() != 0:
+                raise subprocess.CalledProcessError(pr.returncode, cmd)
+        objs = [os.path.join(obj, os.path.splitext(name)[0] + ".o") for name, _ in units]
+        subprocess.check_call([NVCC] + ARCH + ["-shared", "-o", out] + objs)
     syn = os.path.join(ROOT, "synth")
     sout = os.path.join(syn, "libnpswf_synth_cuda.so")
     ssrcs = [os.path.join(syn, "synth_cuda.cu"), os.path.join(syn, "npswf_synth.h")]

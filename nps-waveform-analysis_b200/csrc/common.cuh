@@ -134,6 +134,7 @@ struct DevCalib {
     const int32_t *win_span; // [B] last - first bin of that window
     const double *spline;    // [B][109][4] = y, b, c, d
     const double2 *knots;    // [B][KN_LEN] = (y_i, c_i = y''_i / 2) at knot i - KN_LO, zero outside 0..109
+    const double *knots_x;   // [B][T] the spline's abscissae (interpX, T2:432) when they are not the sample indices; else nullptr
 };
 
 struct KParams {

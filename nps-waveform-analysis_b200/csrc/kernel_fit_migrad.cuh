@@ -1,0 +1,179 @@
+// fit_migrad_kernel: Fitwf (T2:601-828) with the reference's own minimiser -- Minuit2 Migrad on numerical
+// gradients, strategy 1, retry with strategy 2 from the same seeds, fall back to the TSpectrum values -- instead of
+// the Levenberg-Marquardt solver of the other fit kernels.  Same chi2 (ROOT::Fit::Chi2FCN over the BinData of
+// T2:680-688 with Err of T2:946-956), same operation order as a scalar x86-64 build without FMA contraction: this
+// translation unit is compiled with -fmad=false, divisions and square roots are IEEE, and the 90 chi2 terms are
+// summed serially in sample order, so the minimiser sees the function values the reference's Chi2FCN produces and
+// takes the same path (checked bit for bit against the CPU oracle's Migrad restatement in tests/).
+//
+// One warp per fit.  Migrad is sequential, branchy scalar code with a small state (parameters, gradient, P x P
+// inverse-Hessian estimate): lane 0 runs it (migrad_core.hpp) on a shared-memory workspace that no other lane
+// touches; lanes 1..31 sit in a service loop and, for every chi2 evaluation lane 0 asks for, compute the terms of
+// their three samples (spline coefficients of consecutive intervals: one coalesced 1 KB read per pulse); lane 0 adds
+// the 90 terms in order.  The two sides meet at __syncwarp() -- a warp barrier does not need its participants to
+// arrive from the same instruction.  Jobs are claimed one at a time from the per-multiplicity job list.
+#pragma once
+#include "common.cuh"
+#include "migrad_core.hpp"
+
+namespace npswf {
+
+constexpr int MG_WARPS = 8;
+constexpr int MG_THREADS = MG_WARPS * 32;
+// list entries: item | N << MG_NSHIFT (the kernel is instantiated per workspace size, not per multiplicity)
+constexpr int MG_NSHIFT = 27;
+
+template <int PMAX>
+struct MgSmem {
+    mg::Work<PMAX> W;
+    double pe[PMAX];        // parameters of the evaluation in flight
+    double start[PMAX], werr[PMAX];
+    double tk[96];          // the 90 chi2 terms of the evaluation in flight
+    volatile int cmd;       // 1: evaluate at pe, 0: the fit is done
+    int pad;
+};
+
+// this lane's three terms of chi2(pe) -> tk
+template <int PMAX>
+__device__ __forceinline__ void mg_points(MgSmem<PMAX> *sm, int N, int lane, const double *__restrict__ spl,
+                                          const double *__restrict__ knots, const double (&y)[3], const double (&w)[3])
+{
+#pragma unroll
+    for (int kk = 0; kk < 3; kk++) {
+        const int k = lane + 32 * kk;
+        if (k < mg::FIT_NPT) sm->tk[k] = mg::chi2_term(k, sm->pe, N, spl, knots, y[kk], w[kk]);
+    }
+}
+
+// the chi2 functor lane 0 hands to the minimiser
+template <int PMAX>
+struct MgWarpFcn {
+    MgSmem<PMAX> *sm;
+    const double *spl, *knots;
+    int N, P;
+    double y[3], w[3];
+    int ncalls;
+    __device__ __noinline__ double operator()(const double *x)
+    {
+        ncalls++;
+        for (int i = 0; i < P; i++) sm->pe[i] = x[i];
+        sm->cmd = 1;
+        __syncwarp();                                   // release the service lanes
+        mg_points<PMAX>(sm, N, 0, spl, knots, y, w);
+        __syncwarp();                                   // all 90 terms are in tk
+        double chi2 = 0;
+#pragma unroll 6
+        for (int k = 0; k < mg::FIT_NPT; k++) chi2 += sm->tk[k];
+        return chi2;
+    }
+};
+
+template <int PMAX>
+__global__ void __launch_bounds__(MG_THREADS)
+fit_migrad_kernel(const int *__restrict__ job_list, const int *__restrict__ job_count, int *__restrict__ job_next, int list_N,
+                  const double *__restrict__ signal, const double *__restrict__ corr_time_HMS, DevCalib cal, KParams kp,
+                  double *__restrict__ wftime, double *__restrict__ wfampl, double *__restrict__ chi2_out,
+                  double *__restrict__ timewf, double *__restrict__ amplwf, uint8_t *__restrict__ status,
+                  DeviceCounters *__restrict__ ctr)
+{
+    // list_N > 0: every entry of the list is a fit with list_N pulses; list_N == 0: N is packed into the entry
+    extern __shared__ __align__(16) unsigned char mg_smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    MgSmem<PMAX> *sm = reinterpret_cast<MgSmem<PMAX> *>(mg_smem_raw) + warp;
+    const int njobs = *job_count;
+    unsigned long long c_ok1 = 0, c_ok2 = 0, c_fb = 0, c_calls = 0, c_att = 0;
+
+    for (;;) {
+        int job = 0;
+        if (lane == 0) job = atomicAdd(job_next, 1);
+        job = __shfl_sync(0xffffffffu, job, 0);
+        if (job >= njobs) break;
+        const int raw = job_list[job];
+        const int N = list_N > 0 ? list_N : (raw >> MG_NSHIFT) & 15;
+        const long long item = list_N > 0 ? (long long)(raw & (FIT_CONT_RESTART - 1)) : (long long)(raw & ((1 << MG_NSHIFT) - 1));
+        const int P = 2 * N + 1;
+        const long long e = item / B;
+        const int bn = (int)(item % B);
+        const double *sig = signal + (size_t)item * T;
+        const double *spl = cal.spline + (size_t)bn * (T - 1) * 4;
+        const double *knots = cal.knots_x ? cal.knots_x + (size_t)bn * T : nullptr;
+        const double tref = cal.timeref[bn];
+
+        MgWarpFcn<PMAX> fcn;
+        fcn.sm = sm; fcn.spl = spl; fcn.knots = knots; fcn.N = N; fcn.P = P; fcn.ncalls = 0;
+#pragma unroll
+        for (int kk = 0; kk < 3; kk++) {   // BinData (T2:680-688): sample and inverse error
+            const int k = lane + 32 * kk;
+            fcn.y[kk] = 0; fcn.w[kk] = 0;
+            if (k < mg::FIT_NPT) {
+                fcn.y[kk] = sig[mg::FIT_X0 + k];
+                fcn.w[kk] = mg::inv_err(fcn.y[kk]);
+            }
+        }
+        const double *seed_t = wftime + (size_t)item * MAXP, *seed_a = wfampl + (size_t)item * MAXP;
+        mg::FitOutcome out{0, 0.0, 0};
+        __syncwarp();
+        if (lane == 0) {
+            mg::fit_seeds(sig, tref, seed_t, seed_a, N, sm->start);
+            out = mg::fitwf_minimise<PMAX>(fcn, sm->W, N, sm->start, sm->werr);
+            sm->cmd = 0;
+            __syncwarp();
+        } else {
+            for (;;) {
+                __syncwarp();
+                if (sm->cmd == 0) break;
+                mg_points<PMAX>(sm, N, lane, spl, knots, fcn.y, fcn.w);
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+        const int st = __shfl_sync(0xffffffffu, out.status, 0);
+        const double fmin = __shfl_sync(0xffffffffu, out.fmin, 0);
+        const int ncalls = __shfl_sync(0xffffffffu, out.ncalls, 0);
+        // write-back (T2:774-827)
+        const double corr = corr_time_HMS ? corr_time_HMS[e] : 0.0;
+        const double cort = (double)cal.cortime[bn];
+        const double accdt = kp.timerefacc * kp.dt;
+        double out_t = 0, out_a = 0;
+        if (lane < N) {
+            if (st == NPSWF_ST_FALLBACK) {   // TSpectrum values, time converted to corrected ns (T2:779-790)
+                out_t = (seed_t[lane] - tref) * kp.dt + corr - cort - accdt;
+                out_a = seed_a[lane];
+            } else {                         // T2:796-817
+                out_t = sm->W.x[1 + 2 * lane] * kp.dt + corr - cort - accdt;
+                out_a = sm->W.x[2 + 2 * lane];
+            }
+        }
+        __syncwarp();
+        if (lane < N) {
+            wftime[(size_t)item * MAXP + lane] = out_t;
+            wfampl[(size_t)item * MAXP + lane] = out_a;
+        }
+        double bt = out_t, ba = out_a;   // timewf / amplwf: the pulse with the smallest |wftime| (T2:999-1016)
+        for (int p = 1; p < N; p++) {
+            const double tp = __shfl_sync(0xffffffffu, out_t, p), ap = __shfl_sync(0xffffffffu, out_a, p);
+            if (fabs(tp) < fabs(bt)) { bt = tp; ba = ap; }
+        }
+        if (lane == 0) {
+            chi2_out[item] = (st == NPSWF_ST_FALLBACK) ? -100. : fmin / (double)(mg::FIT_NPT - P);   // T2:824-827
+            if (timewf) timewf[item] = bt;
+            if (amplwf) amplwf[item] = ba;
+            if (status) status[item] |= (uint8_t)st;
+        }
+        if (st == NPSWF_ST_FIT_OK1) c_ok1++;
+        else if (st == NPSWF_ST_FIT_OK2) c_ok2++;
+        else c_fb++;
+        c_calls += (unsigned long long)ncalls;
+        c_att++;
+        __syncwarp();
+    }
+    if (ctr && lane == 0) {
+        if (c_att) atomicAdd(&ctr->n_fit_attempted, c_att);
+        if (c_ok1) atomicAdd(&ctr->n_fit_ok_first, c_ok1);
+        if (c_ok2) atomicAdd(&ctr->n_fit_ok_retry, c_ok2);
+        if (c_fb) atomicAdd(&ctr->n_fallback, c_fb);
+        if (c_calls) atomicAdd(&ctr->n_fit_evals, c_calls);
+    }
+}
+
+}  // namespace npswf

@@ -21,6 +21,7 @@
 #include "kernel_fit_small.cuh"
 #include "kernel_fit_thread.cuh"
 #include "kernel_aux.cuh"
+#include "migrad_launch.hpp"
 #include "host_pack.hpp"
 #include <chrono>
 #include <memory>
@@ -79,6 +80,7 @@ struct DevSlot {
     bool fit_thread = true;     // thread-per-fit kernels for N = 1, 2 (env NPSWF_FIT_THREAD=0 selects the sub-warp kernels)
     int occ_fit_thread[5] = {0, 2, 2, 2, 2};   // [4]: N = 4..6
     int fit_thread_maxocc = 0;  // env NPSWF_FIT_THREAD_OCC: cap on resident CTAs per SM (fewer CTAs leave more L1)
+    int occ_migrad[3] = {2, 1, 1};   // fit_migrad_kernel<7, 13, 25>
     int occ_front = 2, occ_search = 4, occ_fit_big = 1, occ_fit_mid = 2, occ_fit_small[4] = {0, 4, 4, 2};  // resident CTAs per SM
     std::vector<cudaEvent_t> prof_events;  // 4 per profiled chunk: start, after front, after search, after fits
     std::vector<cudaEvent_t> prof_pool;
@@ -112,6 +114,7 @@ struct npswf_handle {
     bool chunk_fixed = false;   // cfg.chunk_events given: every path uses exactly that chunk size
     std::mutex mu;
     bool profiling = false;
+    int fit_mode = NPSWF_FIT_FAST;
     int pack_mode = 1;                 // 0 off, 1 auto (on while it is faster than the raw upload), 2 always
     bool chunk_ramp = true;            // env NPSWF_CHUNK_RAMP=0: equal chunks in the host pipeline
     int pack_threads = 0;              // host threads per device
@@ -133,29 +136,38 @@ namespace {
         }                                                                                            \
     } while (0)
 
-// Natural cubic spline through unit-or-arbitrary knots (the curve GSL's gsl_interp_cspline
-// represents), solved with the Thomas algorithm.  coef[i] = {y_i, b_i, c_i, d_i}.
+// Natural cubic spline through the block's knots as GSL builds it for ROOT::Math::Interpolator(kCSPLINE) (T2:612-619;
+// gsl_interp_cspline: cspline_init + gsl_linalg_solve_symm_tridiag): c_0 = c_{n-1} = 0, interior c_i from
+// the symmetric tridiagonal system factorised as L D L^T in GSL's operation order, so the coefficients carry the
+// bits the reference's spline has.  coef[i] = {y_i, b_i, c_i, d_i} for the interval [x_i, x_{i+1}].
 void build_spline(const double *x, const double *y, double *coef)
 {
-    const int n = T;
-    std::vector<double> c(n, 0.0), diag(n), rhs(n), upper(n);
-    // interior equations: h_{i-1} c_{i-1} + 2(h_{i-1}+h_i) c_i + h_i c_{i+1} = 3[(y_{i+1}-y_i)/h_i - (y_i-y_{i-1})/h_{i-1}]
-    for (int i = 1; i < n - 1; i++) {
-        const double h0 = x[i] - x[i - 1], h1 = x[i + 1] - x[i];
-        diag[i] = 2.0 * (h0 + h1);
-        upper[i] = h1;
-        rhs[i] = 3.0 * ((y[i + 1] - y[i]) / h1 - (y[i] - y[i - 1]) / h0);
+    const int n = T, sys = n - 2;
+    std::vector<double> c(n, 0.0), off(sys), diag(sys), rhs(sys), alpha(sys), gamma(sys), z(sys), sol(sys);
+    for (int i = 0; i < sys; i++) {
+        const double h0 = x[i + 1] - x[i], h1 = x[i + 2] - x[i + 1];
+        const double dy0 = y[i + 1] - y[i], dy1 = y[i + 2] - y[i + 1];
+        const double r0 = (h0 != 0.0) ? 1.0 / h0 : 0.0, r1 = (h1 != 0.0) ? 1.0 / h1 : 0.0;
+        off[i] = h1;
+        diag[i] = 2.0 * (h1 + h0);
+        rhs[i] = 3.0 * (dy1 * r1 - dy0 * r0);
     }
-    for (int i = 2; i < n - 1; i++) {  // forward elimination (lower = h_{i-1} = upper[i-1])
-        const double m = upper[i - 1] / diag[i - 1];
-        diag[i] -= m * upper[i - 1];
-        rhs[i] -= m * rhs[i - 1];
+    alpha[0] = diag[0];
+    gamma[0] = off[0] / alpha[0];
+    for (int i = 1; i < sys - 1; i++) {
+        alpha[i] = diag[i] - off[i - 1] * gamma[i - 1];
+        gamma[i] = off[i] / alpha[i];
     }
-    for (int i = n - 2; i >= 1; i--) c[i] = (rhs[i] - upper[i] * c[i + 1]) / diag[i];
+    if (sys > 1) alpha[sys - 1] = diag[sys - 1] - off[sys - 2] * gamma[sys - 2];
+    z[0] = rhs[0];
+    for (int i = 1; i < sys; i++) z[i] = rhs[i] - gamma[i - 1] * z[i - 1];
+    for (int i = 0; i < sys; i++) sol[i] = z[i] / alpha[i];
+    c[sys] = sol[sys - 1];
+    for (int i = sys - 2; i >= 0; i--) c[1 + i] = sol[i] - gamma[i] * c[2 + i];
     for (int i = 0; i < n - 1; i++) {
-        const double h = x[i + 1] - x[i];
+        const double h = x[i + 1] - x[i], dy = y[i + 1] - y[i];
         coef[4 * i + 0] = y[i];
-        coef[4 * i + 1] = (y[i + 1] - y[i]) / h - h * (c[i + 1] + 2.0 * c[i]) / 3.0;
+        coef[4 * i + 1] = (dy / h) - h * (c[i + 1] + 2.0 * c[i]) / 3.0;
         coef[4 * i + 2] = c[i];
         coef[4 * i + 3] = (c[i + 1] - c[i]) / (3.0 * h);
     }
@@ -391,7 +403,12 @@ int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, cons
         const int *list = w.fit_dense + (size_t)N * stride;
         const int *cnt = w.fit_count + N;
         int *next = w.fit_count + 16 + N;  // per-multiplicity job cursor, zeroed with fit_count
-        if (N <= 3 && s.fit_thread) {
+        if (h->fit_mode == NPSWF_FIT_MIGRAD) {
+            // the reference's own minimiser (Migrad, numerical gradients, strategy 1 -> 2), one warp per fit
+            MigradArgs ma{list, cnt, next, N, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr};
+            const int cls = migrad_class(N);
+            CU_TRY(h, migrad_launch(cls, s.sm_count * s.occ_migrad[cls], st, ma));
+        } else if (N <= 3 && s.fit_thread) {
             // thread-per-fit for the first tries of every fit, then the sub-warp kernel on the (rare) fits handed over
             int *ccnt = w.fit_count + 32 + N, *cnext = w.fit_count + 48 + N;
             int *clist = w.cont_list + (size_t)(N - 1) * stride;
@@ -875,6 +892,8 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
     h->kp.fit_max_iter = cfg->fit_max_iter > 0 ? cfg->fit_max_iter : 60;
     h->kp.fit_retry_max_iter = cfg->fit_retry_max_iter > 0 ? cfg->fit_retry_max_iter : 100;
     h->kp.fit_thread_tries = (getenv("NPSWF_FIT_THREAD_TRIES") && atoi(getenv("NPSWF_FIT_THREAD_TRIES")) > 0) ? atoi(getenv("NPSWF_FIT_THREAD_TRIES")) : 20;
+    h->fit_mode = cfg->fit_mode == NPSWF_FIT_MIGRAD ? NPSWF_FIT_MIGRAD : NPSWF_FIT_FAST;
+    if (getenv("NPSWF_FIT_MODE")) h->fit_mode = atoi(getenv("NPSWF_FIT_MODE")) == 1 ? NPSWF_FIT_MIGRAD : NPSWF_FIT_FAST;   // A/B runs of unchanged callers
     h->chunk = cfg->chunk_events > 0 ? cfg->chunk_events : 1184;
     h->chunk_fixed = cfg->chunk_events > 0;
     h->dev_cap = h->chunk_fixed ? h->chunk : 4736;
@@ -1065,6 +1084,8 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_mid, fit_kernel<13>, FIT_THREADS,
                                                          sizeof(FitSmem<13>) * FIT_WARPS));
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_small[1], fit_small_kernel<1, 8, FS_MINB1>, FS_THREADS, 0));
+        CR(migrad_setup(s.occ_migrad));
+        if (s.occ_migrad[0] < 1 || s.occ_migrad[1] < 1 || s.occ_migrad[2] < 1) { h->err = "fit_migrad_kernel does not fit on this device"; return fail(NPSWF_ERR_CUDA); }
         s.fit_thread = !(getenv("NPSWF_FIT_THREAD") && atoi(getenv("NPSWF_FIT_THREAD")) == 0);
         CR(cudaFuncSetAttribute(fit_thread_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
         CR(cudaFuncSetAttribute(fit_thread_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
