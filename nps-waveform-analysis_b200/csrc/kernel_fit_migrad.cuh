@@ -9,7 +9,7 @@
 // One warp per fit.  Migrad is sequential, branchy scalar code with a small state (parameters, gradient, P x P
 // inverse-Hessian estimate): lane 0 runs it (migrad_core.hpp) on a shared-memory workspace that no other lane
 // touches; lanes 1..31 sit in a service loop and, for every chi2 evaluation lane 0 asks for, compute the terms of
-// their three samples (spline coefficients of consecutive intervals: one coalesced 1 KB read per pulse); lane 0 adds
+// their three samples (spline coefficients of consecutive intervals: coalesced reads); lane 0 adds
 // the 90 terms in order.  The two sides meet at __syncwarp() -- a warp barrier does not need its participants to
 // arrive from the same instruction.  Jobs are claimed one at a time from the per-multiplicity job list.
 #pragma once
@@ -24,34 +24,50 @@ constexpr int MG_THREADS = MG_WARPS * 32;
 constexpr int MG_NSHIFT = 27;
 
 template <int PMAX>
-struct MgSmem {
+struct alignas(16) MgSmem {
+    alignas(16) double tk[96];   // the 90 chi2 terms of the evaluation in flight (read back as 16-byte pairs)
     mg::Work<PMAX> W;
     double pe[PMAX];        // parameters of the evaluation in flight
     double start[PMAX], werr[PMAX];
-    double tk[96];          // the 90 chi2 terms of the evaluation in flight
     volatile int cmd;       // 1: evaluate at pe, 0: the fit is done
     int pad;
 };
 
-// this lane's three terms of chi2(pe) -> tk
+// Service lanes 1..31 own the 90 chi2 terms, three each: sample k = (lane - 1) + 31 * kk.  Lane 0 computes none, so
+// that the divergent halves of the warp never issue the same work twice.
+__device__ __forceinline__ int mg_sample(int lane, int kk) { return (lane - 1) + 31 * kk; }
+
+// a service lane's terms of chi2(pe) -> tk
 template <int PMAX>
 __device__ __forceinline__ void mg_points(MgSmem<PMAX> *sm, int N, int lane, const double *__restrict__ spl,
                                           const double *__restrict__ knots, const double (&y)[3], const double (&w)[3])
 {
 #pragma unroll
     for (int kk = 0; kk < 3; kk++) {
-        const int k = lane + 32 * kk;
+        const int k = mg_sample(lane, kk);
         if (k < mg::FIT_NPT) sm->tk[k] = mg::chi2_term(k, sm->pe, N, spl, knots, y[kk], w[kk]);
     }
+}
+
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
 }
 
 // the chi2 functor lane 0 hands to the minimiser
 template <int PMAX>
 struct MgWarpFcn {
     MgSmem<PMAX> *sm;
-    const double *spl, *knots;
-    int N, P;
-    double y[3], w[3];
+    int P;
     int ncalls;
     __device__ __noinline__ double operator()(const double *x)
     {
@@ -59,17 +75,21 @@ struct MgWarpFcn {
         for (int i = 0; i < P; i++) sm->pe[i] = x[i];
         sm->cmd = 1;
         __syncwarp();                                   // release the service lanes
-        mg_points<PMAX>(sm, N, 0, spl, knots, y, w);
         __syncwarp();                                   // all 90 terms are in tk
+        const uint32_t a = smem_u32(sm->tk);
         double chi2 = 0;
-#pragma unroll 6
-        for (int k = 0; k < mg::FIT_NPT; k++) chi2 += sm->tk[k];
+#pragma unroll
+        for (int k = 0; k < mg::FIT_NPT / 2; k++) {     // serial sum in sample order, as FitUtil::EvaluateChi2 does
+            const double2 v = lds_f64x2(a + 16u * (uint32_t)k);
+            chi2 += v.x;
+            chi2 += v.y;
+        }
         return chi2;
     }
 };
 
 template <int PMAX>
-__global__ void __launch_bounds__(MG_THREADS)
+__global__ void __launch_bounds__(MG_THREADS, (PMAX <= 13 ? 3 : 1))
 fit_migrad_kernel(const int *__restrict__ job_list, const int *__restrict__ job_count, int *__restrict__ job_next, int list_N,
                   const double *__restrict__ signal, const double *__restrict__ corr_time_HMS, DevCalib cal, KParams kp,
                   double *__restrict__ wftime, double *__restrict__ wfampl, double *__restrict__ chi2_out,
@@ -100,14 +120,15 @@ fit_migrad_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
         const double tref = cal.timeref[bn];
 
         MgWarpFcn<PMAX> fcn;
-        fcn.sm = sm; fcn.spl = spl; fcn.knots = knots; fcn.N = N; fcn.P = P; fcn.ncalls = 0;
+        fcn.sm = sm; fcn.P = P; fcn.ncalls = 0;
+        double y[3], w[3];
 #pragma unroll
         for (int kk = 0; kk < 3; kk++) {   // BinData (T2:680-688): sample and inverse error
-            const int k = lane + 32 * kk;
-            fcn.y[kk] = 0; fcn.w[kk] = 0;
-            if (k < mg::FIT_NPT) {
-                fcn.y[kk] = sig[mg::FIT_X0 + k];
-                fcn.w[kk] = mg::inv_err(fcn.y[kk]);
+            const int k = mg_sample(lane, kk);
+            y[kk] = 0; w[kk] = 0;
+            if (lane > 0 && k < mg::FIT_NPT) {
+                y[kk] = sig[mg::FIT_X0 + k];
+                w[kk] = mg::inv_err(y[kk]);
             }
         }
         const double *seed_t = wftime + (size_t)item * MAXP, *seed_a = wfampl + (size_t)item * MAXP;
@@ -122,7 +143,7 @@ fit_migrad_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
             for (;;) {
                 __syncwarp();
                 if (sm->cmd == 0) break;
-                mg_points<PMAX>(sm, N, lane, spl, knots, fcn.y, fcn.w);
+                mg_points<PMAX>(sm, N, lane, spl, knots, y, w);
                 __syncwarp();
             }
         }
@@ -167,6 +188,161 @@ fit_migrad_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
         c_att++;
         __syncwarp();
     }
+    if (ctr && lane == 0) {
+        if (c_att) atomicAdd(&ctr->n_fit_attempted, c_att);
+        if (c_ok1) atomicAdd(&ctr->n_fit_ok_first, c_ok1);
+        if (c_ok2) atomicAdd(&ctr->n_fit_ok_retry, c_ok2);
+        if (c_fb) atomicAdd(&ctr->n_fallback, c_fb);
+        if (c_calls) atomicAdd(&ctr->n_fit_evals, c_calls);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// fit_migrad_thread_kernel<N>: the same minimisation, ONE THREAD PER FIT, for N = 1..3 pulses on traces that sit on
+// the ADC lattice (sample = integer count * lsb, T2:357) -- the bulk of the fits.
+//
+// Migrad is scalar code; with a warp per fit 31 lanes idle through it and through the serial chi2 sum.  Here every
+// lane runs its own minimisation (migrad_core.hpp on a thread-private workspace) and evaluates its own chi2 serially
+// in sample order -- the reference's own summation order costs nothing extra -- so a warp advances 32 fits at once
+// wherever their control flow agrees: the seed gradient, the first line-search points, MnHesse.  Where it does not
+// (line-search tails, different iteration counts) lanes wait for one another at the structured join points.
+// Data per thread: the 90 samples as int16 counts in shared memory, transposed [sample][thread]; the sample value is
+// count * lsb (exact), its inverse error comes from a table indexed by |count| built with the same inv_err() at
+// npswf_create.  A trace with a sample off the lattice (or beyond the table) is handed, untouched, to the
+// warp-per-fit kernel above, which takes any doubles.  Both kernels evaluate identical expressions, so which one runs
+// a fit cannot be seen in the result.
+constexpr int MT_THREADS = 128;
+constexpr int MT_WTAB = 8192;        // |count| < MT_WTAB: a 12-bit ADC minus its pedestal stays far inside
+
+template <int N>
+struct MgThreadFcn {
+    const int16_t *col;     // this thread's column of the shared count tile: sample k at col[k * MT_THREADS]
+    const double *wtab;     // inverse error by |count|
+    const double *spl;
+    double lsb;
+    int ncalls;
+    __device__ __noinline__ double operator()(const double *x)
+    {
+        ncalls++;
+        const double p0 = x[0];
+        double t[N], A[N];
+#pragma unroll
+        for (int n = 0; n < N; n++) { t[n] = x[1 + 2 * n]; A[n] = x[2 + 2 * n]; }
+        double chi2 = 0;
+#pragma unroll 2
+        for (int k = 0; k < mg::FIT_NPT; k++) {
+            const int c = col[k * MT_THREADS];
+            const double y = (double)c * lsb;
+            const double w = __ldg(wtab + abs(c));
+            const double xk = (double)(mg::FIT_X0 + k);
+            double val = p0;
+#pragma unroll
+            for (int n = 0; n < N; n++) {
+                const double dt0 = xk - t[n];
+                if (dt0 > 1 && dt0 < mg::FIT_T - 1) {   // T2:629
+                    const int i = (int)dt0;
+                    const double delx = dt0 - (double)i;
+                    const double2 c01 = __ldg(reinterpret_cast<const double2 *>(spl + 4 * i));
+                    const double2 c23 = __ldg(reinterpret_cast<const double2 *>(spl + 4 * i) + 1);
+                    val += A[n] * (c01.x + delx * (c01.y + delx * (c23.x + delx * c23.y)));
+                }
+            }
+            const double tmp = (y - val) * w;
+            chi2 += tmp * tmp;
+        }
+        return chi2;
+    }
+};
+
+__global__ void mg_wtab_kernel(double *wtab, int n, double lsb)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n) wtab[c] = mg::inv_err((double)c * lsb);
+}
+
+template <int N>
+__global__ void __launch_bounds__(MT_THREADS)
+fit_migrad_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_count, int *__restrict__ job_next,
+                         const double *__restrict__ signal, const double *__restrict__ corr_time_HMS, DevCalib cal, KParams kp,
+                         double *__restrict__ wftime, double *__restrict__ wfampl, double *__restrict__ chi2_out,
+                         double *__restrict__ timewf, double *__restrict__ amplwf, uint8_t *__restrict__ status,
+                         DeviceCounters *__restrict__ ctr, const double *__restrict__ wtab, double lsb,
+                         int *__restrict__ ho_count, int *__restrict__ ho_list)
+{
+    constexpr int P = 2 * N + 1;
+    __shared__ int16_t tile[mg::FIT_NPT * MT_THREADS];
+    const int lane = threadIdx.x & 31;
+    const int njobs = *job_count;
+    unsigned long long c_ok1 = 0, c_ok2 = 0, c_fb = 0, c_calls = 0, c_att = 0;
+    mg::Work<P> W;
+    double start[P], werr[P];
+
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(job_next, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= njobs) break;
+        const int job = base + lane;
+        if (job < njobs) {
+            const int raw = job_list[job];
+            const long long item = (long long)(raw & (FIT_CONT_RESTART - 1));
+            const long long e = item / B;
+            const int bn = (int)(item % B);
+            const double *sig = signal + (size_t)item * T;
+            // BinData (T2:680-688) as counts; off the lattice -> the warp-per-fit kernel takes the fit
+            bool lattice = true;
+            for (int k = 0; k < mg::FIT_NPT; k++) {
+                const double y = sig[mg::FIT_X0 + k];
+                const double q = rint(y / lsb);
+                lattice = lattice && (fabs(q) < (double)MT_WTAB) && (q * lsb == y);
+                tile[k * MT_THREADS + threadIdx.x] = (int16_t)(int)q;
+            }
+            if (!lattice) {
+                ho_list[atomicAdd(ho_count, 1)] = raw;
+            } else {
+                MgThreadFcn<N> fcn;
+                fcn.col = tile + threadIdx.x; fcn.wtab = wtab; fcn.spl = cal.spline + (size_t)bn * (T - 1) * 4;
+                fcn.lsb = lsb; fcn.ncalls = 0;
+                const double tref = cal.timeref[bn];
+                double *wt = wftime + (size_t)item * MAXP, *wa = wfampl + (size_t)item * MAXP;
+                mg::fit_seeds(sig, tref, wt, wa, N, start);
+                const mg::FitOutcome out = mg::fitwf_minimise<P>(fcn, W, N, start, werr);
+                // write-back (T2:774-827)
+                const double corr = corr_time_HMS ? corr_time_HMS[e] : 0.0;
+                const double cort = (double)cal.cortime[bn];
+                const double accdt = kp.timerefacc * kp.dt;
+                double bt = 0, ba = 0;
+#pragma unroll
+                for (int p = 0; p < N; p++) {
+                    double ot, oa;
+                    if (out.status == NPSWF_ST_FALLBACK) {   // TSpectrum values, time converted to corrected ns (T2:779-790)
+                        ot = (wt[p] - tref) * kp.dt + corr - cort - accdt;
+                        oa = wa[p];
+                    } else {                                 // T2:796-817
+                        ot = W.x[1 + 2 * p] * kp.dt + corr - cort - accdt;
+                        oa = W.x[2 + 2 * p];
+                    }
+                    wt[p] = ot;
+                    wa[p] = oa;
+                    if (p == 0 || fabs(ot) < fabs(bt)) { bt = ot; ba = oa; }   // T2:999-1016
+                }
+                chi2_out[item] = (out.status == NPSWF_ST_FALLBACK) ? -100. : out.fmin / (double)(mg::FIT_NPT - P);   // T2:824-827
+                if (timewf) timewf[item] = bt;
+                if (amplwf) amplwf[item] = ba;
+                if (status) status[item] |= (uint8_t)out.status;
+                if (out.status == NPSWF_ST_FIT_OK1) c_ok1++;
+                else if (out.status == NPSWF_ST_FIT_OK2) c_ok2++;
+                else c_fb++;
+                c_calls += (unsigned long long)out.ncalls;
+                c_att++;
+            }
+        }
+        __syncwarp();
+    }
+    // per-warp totals -> one atomic each
+    c_att = warp_sum_u64(c_att); c_ok1 = warp_sum_u64(c_ok1); c_ok2 = warp_sum_u64(c_ok2); c_fb = warp_sum_u64(c_fb);
+    c_calls = warp_sum_u64(c_calls);
     if (ctr && lane == 0) {
         if (c_att) atomicAdd(&ctr->n_fit_attempted, c_att);
         if (c_ok1) atomicAdd(&ctr->n_fit_ok_first, c_ok1);

@@ -715,8 +715,14 @@ MG_HD inline double chi2_term(int k, const double *par, int N, const double *spl
             double delx;
             if (knots) { i = knot_interval(knots, dt0); delx = dt0 - knots[i]; }
             else { i = (int)dt0; delx = dt0 - (double)i; }
+#if defined(__CUDA_ARCH__)
+            const double2 c01 = __ldg(reinterpret_cast<const double2 *>(spl + 4 * i));       // 32-byte aligned quads
+            const double2 c23 = __ldg(reinterpret_cast<const double2 *>(spl + 4 * i) + 1);
+            val += par[2 + 2 * p] * (c01.x + delx * (c01.y + delx * (c23.x + delx * c23.y)));
+#else
             const double *c = spl + 4 * i;
             val += par[2 + 2 * p] * (c[0] + delx * (c[1] + delx * (c[2] + delx * c[3])));
+#endif
         }
     }
     const double tmp = (y - val) * w;

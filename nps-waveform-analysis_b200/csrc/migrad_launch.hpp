@@ -16,6 +16,10 @@ struct MigradArgs {
     double *wftime, *wfampl, *chi2, *timewf, *amplwf;
     uint8_t *status;
     DeviceCounters *ctr;
+    // thread-per-fit kernel only: inverse-error table by |count|, the ADC step, the hand-over list for traces off the lattice
+    const double *wtab = nullptr;
+    double lsb = 0;
+    int *ho_count = nullptr, *ho_list = nullptr;
 };
 
 // workspace classes: 0 -> up to 3 pulses (7 parameters), 1 -> up to 6 (13), 2 -> up to 12 (25)
@@ -23,5 +27,10 @@ inline int migrad_class(int N) { return N <= 3 ? 0 : (N <= 6 ? 1 : 2); }
 // shared-memory opt-in + resident CTAs per SM of the three instances (current device)
 cudaError_t migrad_setup(int occ[3]);
 cudaError_t migrad_launch(int cls, int grid, cudaStream_t st, const MigradArgs &a);
+// thread-per-fit instances (N = 1, 2, 3 pulses, lattice traces): resident CTAs per SM, launch, and the table they index
+constexpr int MIGRAD_WTAB_ENTRIES = 8192;
+cudaError_t migrad_thread_setup(int occ[4]);
+cudaError_t migrad_thread_launch(int N, int grid, cudaStream_t st, const MigradArgs &a);
+cudaError_t migrad_build_wtab(double *d_wtab, double lsb, cudaStream_t st);
 
 }  // namespace npswf

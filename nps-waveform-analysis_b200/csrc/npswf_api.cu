@@ -81,6 +81,10 @@ struct DevSlot {
     int occ_fit_thread[5] = {0, 2, 2, 2, 2};   // [4]: N = 4..6
     int fit_thread_maxocc = 0;  // env NPSWF_FIT_THREAD_OCC: cap on resident CTAs per SM (fewer CTAs leave more L1)
     int occ_migrad[3] = {2, 1, 1};   // fit_migrad_kernel<7, 13, 25>
+    int occ_migrad_thread[4] = {0, 4, 4, 4};   // fit_migrad_thread_kernel<1, 2, 3>
+    double *mg_wtab = nullptr;       // inverse error by |ADC count| (thread-per-fit Migrad kernels)
+    double mg_wtab_lsb = 0;          // the ADC step the table was built for
+    bool migrad_thread = true;       // env NPSWF_MIGRAD_THREAD=0: every Migrad fit through the warp-per-fit kernel
     int occ_front = 2, occ_search = 4, occ_fit_big = 1, occ_fit_mid = 2, occ_fit_small[4] = {0, 4, 4, 2};  // resident CTAs per SM
     std::vector<cudaEvent_t> prof_events;  // 4 per profiled chunk: start, after front, after search, after fits
     std::vector<cudaEvent_t> prof_pool;
@@ -407,7 +411,26 @@ int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, cons
             // the reference's own minimiser (Migrad, numerical gradients, strategy 1 -> 2), one warp per fit
             MigradArgs ma{list, cnt, next, N, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr};
             const int cls = migrad_class(N);
-            CU_TRY(h, migrad_launch(cls, s.sm_count * s.occ_migrad[cls], st, ma));
+            if (N <= 3 && s.migrad_thread && s.occ_migrad_thread[N] > 0) {
+                // one thread per fit for traces on the ADC lattice; anything else is handed to the warp-per-fit kernel
+                if (s.mg_wtab_lsb != h->pack_lsb) {   // (re)built on the stream that uses it first; later users are ordered behind it by the fork
+                    CU_TRY(h, migrad_build_wtab(s.mg_wtab, h->pack_lsb, caller));
+                    s.mg_wtab_lsb = h->pack_lsb;
+                    if (conc) {
+                        CU_TRY(h, cudaEventRecord(s.fit_fork, caller));
+                        for (int i = 0; i < 4; i++) CU_TRY(h, cudaStreamWaitEvent(s.fit_stream[i], s.fit_fork, 0));
+                    }
+                }
+                ma.wtab = s.mg_wtab; ma.lsb = h->pack_lsb;
+                ma.ho_count = w.fit_count + 32 + N;
+                ma.ho_list = w.cont_list + (size_t)(N - 1) * stride;
+                CU_TRY(h, migrad_thread_launch(N, s.sm_count * s.occ_migrad_thread[N], st, ma));
+                MigradArgs mb = ma;
+                mb.job_list = ma.ho_list; mb.job_count = ma.ho_count; mb.job_next = w.fit_count + 48 + N;
+                CU_TRY(h, migrad_launch(cls, s.sm_count * s.occ_migrad[cls], st, mb));
+            } else {
+                CU_TRY(h, migrad_launch(cls, s.sm_count * s.occ_migrad[cls], st, ma));
+            }
         } else if (N <= 3 && s.fit_thread) {
             // thread-per-fit for the first tries of every fit, then the sub-warp kernel on the (rare) fits handed over
             int *ccnt = w.fit_count + 32 + N, *cnext = w.fit_count + 48 + N;
@@ -1085,6 +1108,9 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
                                                          sizeof(FitSmem<13>) * FIT_WARPS));
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_small[1], fit_small_kernel<1, 8, FS_MINB1>, FS_THREADS, 0));
         CR(migrad_setup(s.occ_migrad));
+        CR(migrad_thread_setup(s.occ_migrad_thread));
+        s.migrad_thread = !(getenv("NPSWF_MIGRAD_THREAD") && atoi(getenv("NPSWF_MIGRAD_THREAD")) == 0);
+        if ((rc = dev_alloc(h, s, &s.mg_wtab, (size_t)MIGRAD_WTAB_ENTRIES))) return fail(rc);
         if (s.occ_migrad[0] < 1 || s.occ_migrad[1] < 1 || s.occ_migrad[2] < 1) { h->err = "fit_migrad_kernel does not fit on this device"; return fail(NPSWF_ERR_CUDA); }
         s.fit_thread = !(getenv("NPSWF_FIT_THREAD") && atoi(getenv("NPSWF_FIT_THREAD")) == 0);
         CR(cudaFuncSetAttribute(fit_thread_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));

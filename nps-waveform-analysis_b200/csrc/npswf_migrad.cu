@@ -39,4 +39,37 @@ cudaError_t migrad_launch(int cls, int grid, cudaStream_t st, const MigradArgs &
     return cudaGetLastError();
 }
 
+cudaError_t migrad_thread_setup(int occ[4])
+{
+    static_assert(MIGRAD_WTAB_ENTRIES == MT_WTAB, "table size");
+    cudaError_t e;
+    occ[0] = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], fit_migrad_thread_kernel<1>, MT_THREADS, 0)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], fit_migrad_thread_kernel<2>, MT_THREADS, 0)) != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[3], fit_migrad_thread_kernel<3>, MT_THREADS, 0);
+}
+
+template <int N>
+static void launch_thread(int grid, cudaStream_t st, const MigradArgs &a)
+{
+    fit_migrad_thread_kernel<N><<<grid, MT_THREADS, 0, st>>>(a.job_list, a.job_count, a.job_next, a.signal, a.corr, a.cal, a.kp,
+                                                            a.wftime, a.wfampl, a.chi2, a.timewf, a.amplwf, a.status, a.ctr,
+                                                            a.wtab, a.lsb, a.ho_count, a.ho_list);
+}
+
+cudaError_t migrad_thread_launch(int N, int grid, cudaStream_t st, const MigradArgs &a)
+{
+    if (grid <= 0) return cudaSuccess;
+    if (N == 1) launch_thread<1>(grid, st, a);
+    else if (N == 2) launch_thread<2>(grid, st, a);
+    else launch_thread<3>(grid, st, a);
+    return cudaGetLastError();
+}
+
+cudaError_t migrad_build_wtab(double *d_wtab, double lsb, cudaStream_t st)
+{
+    mg_wtab_kernel<<<(MT_WTAB + 255) / 256, 256, 0, st>>>(d_wtab, MT_WTAB, lsb);
+    return cudaGetLastError();
+}
+
 }  // namespace npswf
