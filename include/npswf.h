@@ -59,8 +59,6 @@ typedef struct NpsWfConfig {
     int32_t fit_max_iter;   /* LM iterations of the first attempt; 0 = default            */
     int32_t fit_retry_max_iter; /* LM iterations of the retry; 0 = default                */
     int32_t fit_mode;       /* NPSWF_FIT_FAST (0, default) or NPSWF_FIT_MIGRAD: minimiser of Fitwf, see below */
-    double fit_arb_chi2;    /* FAST mode: fits ending with chi2/ndf above this are redone by the Migrad kernel from
-                               their seeds (0 = library default, < 0 = never)                                  */
 } NpsWfConfig;
 
 /* Minimiser of Fitwf (T2:693-773).

@@ -35,8 +35,7 @@ class NpsWfConfig(C.Structure):
     _fields_ = [("specthres", C.c_double), ("mfthres", C.c_double), ("trig_thres", C.c_double),
                 ("coinc_width", C.c_int32), ("dt", C.c_double), ("timerefacc", C.c_double),
                 ("n_devices", C.c_int32), ("devices", C.POINTER(C.c_int32)), ("chunk_events", C.c_int32),
-                ("fit_max_iter", C.c_int32), ("fit_retry_max_iter", C.c_int32), ("fit_mode", C.c_int32),
-                ("fit_arb_chi2", C.c_double)]
+                ("fit_max_iter", C.c_int32), ("fit_retry_max_iter", C.c_int32), ("fit_mode", C.c_int32)]
 
 
 class NpsWfCalib(C.Structure):
@@ -160,15 +159,14 @@ class NpsWf:
     """Handle over (tunables, calibration) — the reference's file-scope globals (T2:51-85)."""
 
     def __init__(self, calib, specthres=0.02, mfthres=1.5, trig_thres=10.0, coinc_width=20, dt=4.0,
-                 timerefacc=0.0, devices=None, chunk_events=0, fit_max_iter=0, fit_retry_max_iter=0, fit_mode=FIT_FAST,
-                 fit_arb_chi2=0.0):
+                 timerefacc=0.0, devices=None, chunk_events=0, fit_max_iter=0, fit_retry_max_iter=0, fit_mode=FIT_FAST):
         L = lib()
         cfg = NpsWfConfig()
         L.npswf_default_config(C.byref(cfg))
         cfg.specthres, cfg.mfthres, cfg.trig_thres = specthres, mfthres, trig_thres
         cfg.coinc_width, cfg.dt, cfg.timerefacc = coinc_width, dt, timerefacc
         cfg.chunk_events, cfg.fit_max_iter, cfg.fit_retry_max_iter = chunk_events, fit_max_iter, fit_retry_max_iter
-        cfg.fit_mode, cfg.fit_arb_chi2 = fit_mode, fit_arb_chi2
+        cfg.fit_mode = fit_mode
         self.chunk_events = chunk_events if chunk_events > 0 else 1184   # library default (events per chunk)
         self._dev = None
         if devices is not None:

@@ -154,7 +154,9 @@ def test_cluster_threshold_off_lattice_and_near_threshold(gpu, orc):
         assert np.array_equal(ok[e], ref)
 
 
-@pytest.mark.parametrize("cfg,min_frac", [(1, 0.999), (2, 0.99), (3, 0.80)])
+# FAST (LM) mode on the small fixtures (3 events per config: ~3 000 fits, so +-0.5 point of statistical width in
+# config 3); the gates at BASELINE size, and the MIGRAD mode's bit-for-bit comparison, are in test_gpu_migrad.py
+@pytest.mark.parametrize("cfg,min_frac", [(1, 0.999), (2, 0.993), (3, 0.925)])
 def test_analyze_vs_oracle(gpu, orc, events, cfg, min_frac):
     ev = events[cfg]
     ref = orc.analyze_batch(ev["signal"], ev["pres"], ev["corr_time_HMS"], n_threads=8)
@@ -169,10 +171,6 @@ def test_analyze_vs_oracle(gpu, orc, events, cfg, min_frac):
         cfg, n_both, frac, int(((got["status"] & 16) > 0).sum()), int(((ref["status"] & 16) > 0).sum())))
     assert n_both > 0.5 * ((ref["status"] & 2) > 0).sum()
     assert frac >= min_frac
-    # where the two minimisers disagree, the GPU must not sit at a worse chi2 than Migrad more often than not
-    bad = both & ~good
-    if bad.sum() > 20:
-        assert (got["chi2"][bad] <= ref["chi2"][bad] * (1 + 1e-3)).mean() > 0.3
     # timewf / amplwf are the pulse with the smallest |wftime| (T2:999-1016)
     fit = (got["status"] & 28) > 0
     tt = np.where(np.arange(12)[None, None, :] < got["wfnpulse"][..., None], np.abs(got["wftime"]), np.inf)
@@ -222,8 +220,8 @@ def test_stage_fitwf_equals_pipeline(gpu, events):
     assert np.array_equal(r["chi2"][fitted], full["chi2"][fitted])
 
 
-@pytest.mark.parametrize("name,min_frac", [("cfg1_acc0", 0.999), ("cfg2_acc0", 0.99), ("cfg2_accm5", 0.99),
-                                           ("cfg3_acc0", 0.80)])
+@pytest.mark.parametrize("name,min_frac", [("cfg1_acc0", 0.999), ("cfg2_acc0", 0.993), ("cfg2_accm5", 0.993),
+                                           ("cfg3_acc0", 0.925)])
 def test_against_golden_fixture(pkg, name, min_frac):
     g = np.load(golden_path(name + ".npz"))
     c = np.load(golden_path("calib.npz"))
@@ -243,6 +241,11 @@ def test_against_golden_fixture(pkg, name, min_frac):
     n_both, frac, _, _ = _fit_agreement(ref, got)
     print("%s: both-converged %d, within tolerance %.5f" % (name, n_both, frac))
     assert frac >= min_frac
+    # MIGRAD fit mode: the committed oracle outputs, bit for bit
+    hm = pkg.NpsWf(cal, timerefacc=float(g["timerefacc"]), fit_mode=pkg.FIT_MIGRAD)
+    gm = hm.analyze_i16(g["counts"], synth.LSB, g["pres"], g["corr"])
+    for k in ("wfnpulse", "status", "wftime", "wfampl", "chi2", "timewf", "amplwf"):
+        assert np.array_equal(gm[k], g[k]), (name, k)
 
 
 def test_size_independent_properties(gpu, calib, spline):
