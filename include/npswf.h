@@ -137,6 +137,14 @@ int npswf_analyze_batch_i16(npswf_handle *h, int64_t n_events, const int16_t *co
                             const int32_t *pres, const double *corr_time_HMS, int32_t *wfnpulse, double *wftime,
                             double *wfampl, double *chi2, double *timewf, double *amplwf, uint8_t *status);
 
+/* int16 ADC counts in, the reference's own output packing out (npswf_analyze_batch_i16 + npswf_analyze_batch_flat):
+ * the leanest host transport -- about 250 B per block-waveform cross PCIe instead of 1 100 -- and what a reader that
+ * already holds the raw fADC counts should call. */
+int npswf_analyze_batch_flat_i16(npswf_handle *h, int64_t n_events, const int16_t *counts, double lsb_mV, const int32_t *pres,
+                                 const double *corr_time_HMS, int32_t *wfnpulse, int64_t *pulse_offset, int32_t *pulse_count,
+                                 double *wftime_pool, double *wfampl_pool, int64_t pool_capacity, double *chi2, double *timewf,
+                                 double *amplwf, uint8_t *status, int64_t *n_pulses);
+
 /* Transport of npswf_analyze_batch's binary64 traces.  The reference's samples are ADC counts * ADCtomV (1000/4096 mV,
  * T2:357), so a chunk is sent to the device as int16 counts whenever that reproduces every double of the chunk bit for
  * bit (checked sample by sample by `n_threads` host threads while the device works on the previous chunk); any other

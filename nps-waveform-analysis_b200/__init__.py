@@ -58,6 +58,7 @@ EXPORTS = [
     "npswf_device_timeref", "npswf_flatten_event", "npswf_debug_exp", "npswf_debug_exact_ops", "npswf_debug_fp64_peak", "npswf_unpack_batch", "npswf_analyze_batch_packed",
     "npswf_event_diagnostics_batch", "npswf_event_diagnostics_device", "npswf_set_profiling",
     "npswf_get_stage_times", "npswf_set_host_packing", "npswf_host_packing_stats", "npswf_debug_pack_counts", "npswf_analyze_batch_flat",
+    "npswf_analyze_batch_flat_i16",
 ]
 
 _lib = None
@@ -286,6 +287,22 @@ class NpsWf:
             self.h, C.c_int64(E), _p(sig), _p(pr), _p(co), _p(out["wfnpulse"]), _p(out["pulse_offset"]), _p(out["pulse_count"]),
             _p(out["wftime_pool"]), _p(out["wfampl_pool"]), C.c_int64(out["wftime_pool"].size), _p(out["chi2"]),
             _p(out["timewf"]), _p(out["amplwf"]), _p(out["status"]), C.byref(npul)))
+        out["n_pulses"] = npul.value
+        return out
+
+    def analyze_flat_i16(self, counts, lsb_mV, pres, corr_time_HMS, capacity=None, out=None):
+        """analyze_flat() on int16 ADC counts: the leanest host transport in both directions."""
+        cn = _c(counts, np.int16).reshape(-1, NBLOCKS, NTIME)
+        E = cn.shape[0]
+        pr = _c(pres, np.int32).reshape(E, NBLOCKS)
+        co = _c(corr_time_HMS, np.float64).reshape(E)
+        if out is None:
+            out = self.alloc_flat_outputs(E, capacity if capacity is not None else E * NBLOCKS * MAXWFPULSES)
+        npul = C.c_int64(0)
+        self._check(lib().npswf_analyze_batch_flat_i16(
+            self.h, C.c_int64(E), _p(cn), C.c_double(lsb_mV), _p(pr), _p(co), _p(out["wfnpulse"]), _p(out["pulse_offset"]),
+            _p(out["pulse_count"]), _p(out["wftime_pool"]), _p(out["wfampl_pool"]), C.c_int64(out["wftime_pool"].size),
+            _p(out["chi2"]), _p(out["timewf"]), _p(out["amplwf"]), _p(out["status"]), C.byref(npul)))
         out["n_pulses"] = npul.value
         return out
 

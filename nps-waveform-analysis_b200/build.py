@@ -33,10 +33,18 @@ def build(force=False, verbose=False):
         os.makedirs(obj, exist_ok=True)
         vflag = ["-Xptxas", "-v"] if verbose else []
         units = [("npswf_api.cu", []), ("npswf_migrad.cu", ["-fmad=false"]), ("host_pack.cpp", [])]
+        hdr = os.path.join(ROOT, "include", "npswf.h")
+        migrad_only = {"npswf_migrad.cu", "kernel_fit_migrad.cuh", "migrad_core.hpp"}
+        deps = {
+            "npswf_migrad.cu": [os.path.join(csrc, f) for f in ("npswf_migrad.cu", "kernel_fit_migrad.cuh", "migrad_core.hpp",
+                                                                "migrad_launch.hpp", "common.cuh")] + [hdr],
+            "host_pack.cpp": [os.path.join(csrc, f) for f in ("host_pack.cpp", "host_pack.hpp")],
+            "npswf_api.cu": [os.path.join(csrc, f) for f in sorted(os.listdir(csrc)) if f not in migrad_only] + [hdr],
+        }
         procs = []
         for name, extra in units:
             o = os.path.join(obj, os.path.splitext(name)[0] + ".o")
-            if force or _stale(o, srcs):
+            if force or _stale(o, deps[name]):
                 cmd = [NVCC] + ARCH + [f for f in COMMON if f != "-shared"] + vflag + extra + ["-c", "-o", o, os.path.join(csrc, name)]
                 procs.append((cmd, subprocess.Popen(cmd)))
         for cmd, pr in procs:

@@ -21,13 +21,21 @@ constexpr int NDATA_MAX = NSLOTS * (T + 2);        // T2:356
 // a slot outside [0, 1104) ends the event (T2:867-872); an event with more than 1104*112 words is skipped entirely
 // (T2:830-836).  Not kept: pres[bloc] = 1 for bloc in [1080, 1104) writes past the reference's
 // 1080-entry vector; samples beyond it = 109 would overwrite the next block.
+// Int_t x = <double>: truncation toward zero; NaN and values beyond the int range give INT_MIN, what the x86-64
+// conversion of the reference's build produces (`Int_t bloc, nsamp`, T2:553, 857-859)
+__device__ __forceinline__ int to_int_t(double v)
+{
+    return (v > -2147483649.0 && v < 2147483648.0) ? (int)v : (int)0x80000000;
+}
+
 __global__ void __launch_bounds__(UNPACK_THREADS)
 unpack_kernel(const double *__restrict__ samp, const long long *__restrict__ offsets, long long base, long long n_events,
               double *__restrict__ signal, int32_t *__restrict__ pres)
 {
     __shared__ int s_pos[NSLOTS + 1];     // word index of the record's first sample
     __shared__ short s_bloc[NSLOTS + 1], s_ns[NSLOTS + 1];
-    __shared__ int s_nrec;
+    __shared__ int s_nrec, s_more;
+    __shared__ long long s_next;          // where the header walk continues in the next round
     __shared__ int s_cnt[NSLOTS];         // records per slot
     for (long long e = blockIdx.x; e < n_events; e += gridDim.x) {
         const double *S = samp + (offsets[e] - base);   // samp holds the words from offset `base` on
@@ -40,52 +48,61 @@ unpack_kernel(const double *__restrict__ samp, const long long *__restrict__ off
         // warm the cache lines of the nominal header positions
         for (long long k = threadIdx.x; k * (T + 2) + 1 < N && k < NSLOTS; k += UNPACK_THREADS)
             asm volatile("prefetch.global.L1 [%0];" ::"l"(S + k * (T + 2)));
+        if (threadIdx.x == 0) s_next = 0;
         __syncthreads();
-        if (threadIdx.x == 0) {
-            long long ns = 0;
-            int nrec = 0;
-            while (ns + 1 < N && nrec < NSLOTS) {     // (a header needs two words)
-                double bloc = S[ns];
-                const int nsamp = (int)S[ns + 1];
-                ns += 2;
-                if (bloc == 2000) bloc = 1080;
-                if (bloc == 2001) bloc = 1081;
-                if (bloc < 0 || bloc > NSLOTS - 0.5) break;                                 // T2:867-872
-                s_pos[nrec] = (int)ns;
-                s_bloc[nrec] = (short)(int)bloc;
-                s_ns[nrec] = (short)max(0, min(nsamp, 32767));
-                nrec++;
-                ns += max(nsamp, 0);
+        // Rounds of up to NSLOTS records (one round for any well-formed event; a malformed stream of short or empty
+        // records can hold up to N / 2 of them): the walk continues until the words run out, as the reference's does.
+        for (;;) {
+            if (threadIdx.x == 0) {
+                long long ns = s_next;
+                int nrec = 0, more = 0;
+                while (ns + 1 < N) {                  // (a header needs two words)
+                    if (nrec == NSLOTS) { more = 1; break; }
+                    int bloc = to_int_t(S[ns]);
+                    const int nsamp = to_int_t(S[ns + 1]);
+                    ns += 2;
+                    if (bloc == 2000) bloc = 1080;
+                    if (bloc == 2001) bloc = 1081;
+                    if (bloc < 0 || bloc > NSLOTS - 1) { ns = N; break; }                   // T2:867-872: ends the event
+                    s_pos[nrec] = (int)ns;
+                    s_bloc[nrec] = (short)bloc;
+                    s_ns[nrec] = (short)max(0, min(nsamp, 32767));
+                    nrec++;
+                    ns += max(nsamp, 0);
+                }
+                s_nrec = nrec;
+                s_more = more;
+                s_next = ns;
             }
-            s_nrec = nrec;
-        }
-        __syncthreads();
-        const int nrec = s_nrec;
-        for (int i = threadIdx.x; i < NSLOTS; i += UNPACK_THREADS) s_cnt[i] = 0;
-        __syncthreads();
-        for (int r = threadIdx.x; r < nrec; r += UNPACK_THREADS) atomicAdd(&s_cnt[s_bloc[r]], 1);
-        __syncthreads();
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        // slots that occur once (all of them in a well-formed event): one warp per record, any order
-        for (int r = warp; r < nrec; r += UNPACK_THREADS / 32) {
-            const int b = s_bloc[r];
-            if (b < B && s_cnt[b] == 1) {
-                if (lane == 0) pr[b] = 1;                                                   // T2:877
-                for (int it = lane; it < s_ns[r] && it < T && s_pos[r] + it < N; it += 32) sig[b * T + it] = S[s_pos[r] + it];
-            }
-        }
-        // a slot that occurs more than once ends with the samples of its later records: stream order, one warp
-        if (warp == 0) {
-            for (int r = 0; r < nrec; r++) {
+            for (int i = threadIdx.x; i < NSLOTS; i += UNPACK_THREADS) s_cnt[i] = 0;
+            __syncthreads();
+            const int nrec = s_nrec;
+            for (int r = threadIdx.x; r < nrec; r += UNPACK_THREADS) atomicAdd(&s_cnt[s_bloc[r]], 1);
+            __syncthreads();
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            // slots that occur once in the round (all of them in a well-formed event): one warp per record, any order
+            for (int r = warp; r < nrec; r += UNPACK_THREADS / 32) {
                 const int b = s_bloc[r];
-                if (b < B && s_cnt[b] > 1) {
-                    if (lane == 0) pr[b] = 1;
+                if (b < B && s_cnt[b] == 1) {
+                    if (lane == 0) pr[b] = 1;                                               // T2:877
                     for (int it = lane; it < s_ns[r] && it < T && s_pos[r] + it < N; it += 32) sig[b * T + it] = S[s_pos[r] + it];
-                    __syncwarp();
                 }
             }
+            // a slot that occurs more than once ends with the samples of its later records: stream order, one warp
+            if (warp == 0) {
+                for (int r = 0; r < nrec; r++) {
+                    const int b = s_bloc[r];
+                    if (b < B && s_cnt[b] > 1) {
+                        if (lane == 0) pr[b] = 1;
+                        for (int it = lane; it < s_ns[r] && it < T && s_pos[r] + it < N; it += 32) sig[b * T + it] = S[s_pos[r] + it];
+                        __syncwarp();
+                    }
+                }
+            }
+            __syncthreads();     // the round's copies are done before the next round (stream order across rounds) / the next event
+            if (!s_more) break;
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 

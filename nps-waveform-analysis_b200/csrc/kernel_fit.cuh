@@ -201,7 +201,7 @@ __device__ __forceinline__ LmOutcome lm_warp(FitSmem<PMAX> *sm, int N, int P, in
             }
             __syncwarp();
         }
-        if (!accepted) { converged = true; break; }
+        if (!accepted) { converged = isfinite(chi2); break; }   // no descent step left; a chi2 that is not a number is a failed attempt
         if (converged) break;
     }
     return {converged, chi2, it + 1};

@@ -212,7 +212,18 @@ fit_migrad_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
 // npswf_create.  A trace with a sample off the lattice (or beyond the table) is handed, untouched, to the
 // warp-per-fit kernel above, which takes any doubles.  Both kernels evaluate identical expressions, so which one runs
 // a fit cannot be seen in the result.
-constexpr int MT_THREADS = 128;
+#ifndef NPSWF_MT_THREADS
+#define NPSWF_MT_THREADS 128
+#endif
+#ifndef NPSWF_MT_MINBLOCKS
+#define NPSWF_MT_MINBLOCKS 2
+#endif
+#ifdef NPSWF_MT_FCN_INLINE
+#define MT_FCN_ATTR __forceinline__
+#else
+#define MT_FCN_ATTR __noinline__
+#endif
+constexpr int MT_THREADS = NPSWF_MT_THREADS;
 constexpr int MT_WTAB = 8192;        // |count| < MT_WTAB: a 12-bit ADC minus its pedestal stays far inside
 
 template <int N>
@@ -222,7 +233,7 @@ struct MgThreadFcn {
     const double *spl;
     double lsb;
     int ncalls;
-    __device__ __noinline__ double operator()(const double *x)
+    __device__ MT_FCN_ATTR double operator()(const double *x)
     {
         ncalls++;
         const double p0 = x[0];
@@ -262,7 +273,7 @@ __global__ void mg_wtab_kernel(double *wtab, int n, double lsb)
 }
 
 template <int N>
-__global__ void __launch_bounds__(MT_THREADS)
+__global__ void __launch_bounds__(MT_THREADS, NPSWF_MT_MINBLOCKS)
 fit_migrad_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_count, int *__restrict__ job_next,
                          const double *__restrict__ signal, const double *__restrict__ corr_time_HMS, DevCalib cal, KParams kp,
                          double *__restrict__ wftime, double *__restrict__ wfampl, double *__restrict__ chi2_out,

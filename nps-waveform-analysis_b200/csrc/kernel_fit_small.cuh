@@ -377,7 +377,17 @@ fit_small_kernel(const int *__restrict__ job_list, const int *__restrict__ job_c
             } else {
                 lambda = fmax(lambda * 10, 1e-6);
                 rejects++;
-                if (rejects >= 30) { converged = true; finished = true; iters++; }  // no descent step left
+                if (rejects >= 30) {   // no descent step left: a minimum to machine precision -- unless chi2 is not a number
+                    if (isfinite(cur.c2)) { converged = true; finished = true; iters++; }
+                    else if (attempt == 1) {   // (NaN / Inf sample, Cholesky failing on every try): failed attempt, as Migrad's !ok (T2:755-768)
+#pragma unroll
+                        for (int i = 0; i < P; i++) par[i] = seed[i];
+                        fresh = true; lambda = 1.0; attempt = 2; max_iter = kp.fit_retry_max_iter; newton = false;
+                        it_total += iters; iters = 0; rejects = 0;
+                    } else {
+                        finished = true;
+                    }
+                }
             }
         }
         // ---- write back finished fits

@@ -332,7 +332,10 @@ fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
             } else {
                 lambda = fmax(lambda * 10, 1e-6);
                 rejects++;
-                if (rejects >= 30) { finished = true; iters++; }  // no descent step left
+                if (rejects >= 30) {   // no descent step left; a chi2 that is not a number goes through the retry policy of the sub-warp kernel
+                    if (isfinite(cur.c2)) { finished = true; iters++; }
+                    else handoff = true;
+                }
             }
             bool restart = false;
             if (!finished && !handoff && tries >= max_tries) { handoff = true; restart = N >= 4; }

@@ -84,6 +84,8 @@ struct DevSlot {
     int occ_migrad_thread[4] = {0, 4, 4, 4};   // fit_migrad_thread_kernel<1, 2, 3>
     double *mg_wtab = nullptr;       // inverse error by |ADC count| (thread-per-fit Migrad kernels)
     double mg_wtab_lsb = 0;          // the ADC step the table was built for
+    cudaEvent_t last_use = nullptr;  // end of the last device-path call: later calls order themselves behind it (shared scratch, job lists, fit streams)
+    bool last_use_valid = false;
     bool migrad_thread = true;       // env NPSWF_MIGRAD_THREAD=0: every Migrad fit through the warp-per-fit kernel
     int occ_front = 2, occ_search = 4, occ_fit_big = 1, occ_fit_mid = 2, occ_fit_small[4] = {0, 4, 4, 2};  // resident CTAs per SM
     std::vector<cudaEvent_t> prof_events;  // 4 per profiled chunk: start, after front, after search, after fits
@@ -129,13 +131,29 @@ struct npswf_handle {
 
 namespace {
 
+// temporary device buffer of the synchronous tap / stage entry points: freed on every return path
+template <class Tp>
+struct DevBuf {
+    Tp *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t count) { return cudaMalloc((void **)&p, std::max<size_t>(count, 1) * sizeof(Tp)); }
+    operator Tp *() const { return p; }
+};
+
+// several device threads of one call may fail at once (for_each_slot_range): the message is written under the handle's mutex
+void set_error(npswf_handle *h, const char *msg)
+{
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->err = msg;
+}
+
 #define CU_TRY(h, expr)                                                                              \
     do {                                                                                             \
         cudaError_t _e = (expr);                                                                     \
         if (_e != cudaSuccess) {                                                                     \
             char _b[512];                                                                            \
             snprintf(_b, sizeof _b, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
-            (h)->err = _b;                                                                           \
+            set_error(h, _b);                                                                        \
             return NPSWF_ERR_CUDA;                                                                   \
         }                                                                                            \
     } while (0)
@@ -183,7 +201,7 @@ int dev_alloc(npswf_handle *h, DevSlot &s, Tp **p, size_t count)
     void *q = nullptr;
     cudaError_t e = cudaMalloc(&q, count * sizeof(Tp));
     if (e != cudaSuccess) {
-        h->err = std::string("cudaMalloc failed: ") + cudaGetErrorString(e);
+        set_error(h, (std::string("cudaMalloc failed: ") + cudaGetErrorString(e)).c_str());
         return NPSWF_ERR_NOMEM;
     }
     s.owned.push_back(q);
@@ -539,12 +557,13 @@ int run_chunk(npswf_handle *h, DevSlot &s, Workspace &w, cudaStream_t st, int64_
 int fold_profile(npswf_handle *h, DevSlot &s)
 {
     for (size_t i = 0; i + 3 < s.prof_events.size(); i += 4) {
-        for (int k = 0; k < 3; k++) {
-            float ms = 0;
-            CU_TRY(h, cudaEventElapsedTime(&ms, s.prof_events[i + k], s.prof_events[i + k + 1]));
-            h->stage_ms[k] += ms;
+        float ms[3] = {0, 0, 0};
+        for (int k = 0; k < 3; k++) CU_TRY(h, cudaEventElapsedTime(&ms[k], s.prof_events[i + k], s.prof_events[i + k + 1]));
+        {
+            std::lock_guard<std::mutex> lk(h->mu);   // one thread per device folds into the handle's totals
+            for (int k = 0; k < 3; k++) h->stage_ms[k] += ms[k];
+            h->stage_chunks++;
         }
-        h->stage_chunks++;
         for (int k = 0; k < 4; k++) s.prof_pool.push_back(s.prof_events[i + k]);
     }
     s.prof_events.clear();
@@ -588,13 +607,38 @@ struct HostIO {
     int64_t *pulses_out = nullptr;   // [n_devices]: pulses written by each device range
 };
 
-// Chunked, double-buffered host pipeline on one device for events [lo, hi).
+// Every call works on per-slot state shared by all calls (scratch, job lists and cursors, fit streams, fork / join
+// events).  The device-path call is asynchronous on the caller's stream, so it leaves an event behind; a host-buffer
+// call waits for it on the host, the next device-path call makes its stream wait for it -- calls on different
+// streams are thereby serialised instead of corrupting one another's job lists.
+int wait_last_use(npswf_handle *h, DevSlot &s)
+{
+    if (s.last_use_valid) CU_TRY(h, cudaEventSynchronize(s.last_use));
+    return 0;
+}
+
+int analyze_range_impl(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &io);
+
+// Chunked, double-buffered host pipeline on one device for events [lo, hi).  On any error nothing is left in flight
+// that still reads or writes the caller's buffers.
 int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &io)
+{
+    const int rc = analyze_range_impl(h, d, lo, hi, io);
+    if (rc) {
+        cudaSetDevice(h->slots[d].device);
+        cudaDeviceSynchronize();
+        (void)cudaGetLastError();
+    }
+    return rc;
+}
+
+int analyze_range_impl(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &io)
 {
     DevSlot &s = h->slots[d];
     CU_TRY(h, cudaSetDevice(s.device));
-    int rc = ensure_io(h, s);
+    int rc = wait_last_use(h, s);
     if (rc) return rc;
+    if ((rc = ensure_io(h, s))) return rc;
     // Host buffers: a three-stage pipeline over the two workspaces -- uploads on their own stream, every kernel on
     // the chunk's own stream, downloads on a
     // third stream -- so the copy engines of both directions run under the kernels of the neighbouring chunks.
@@ -671,7 +715,7 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
             char b[256];
             snprintf(b, sizeof b, "npswf_analyze_batch_flat: pulse pool too small (events %lld..%lld need %lld more pulses, %lld left in "
                      "this range's share)", (long long)pend.e0, (long long)(pend.e0 + pend.n), (long long)total, (long long)(pool_hi - pool_cur));
-            h->err = b;
+            set_error(h, b);
             cudaDeviceSynchronize();   // leave nothing in flight that still reads or writes the caller's buffers
             pend.w = nullptr;
             pend2.w = nullptr;
@@ -777,6 +821,8 @@ int analyze_range(npswf_handle *h, int d, int64_t lo, int64_t hi, const HostIO &
             }
             if (words > w.packed_cap) {   // grows to the largest chunk seen (a full event is 1104 * 112 words)
                 CU_TRY(h, cudaStreamSynchronize(s_cmp));
+                CU_TRY(h, cudaStreamSynchronize(s_in));
+                dev_free(s, &w.packed);
                 if ((rc = dev_alloc(h, s, &w.packed, words + words / 4 + 1))) return rc;
                 w.packed_cap = words + words / 4 + 1;
             }
@@ -1087,6 +1133,7 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
         CR(cudaStreamCreateWithFlags(&s.copy_out, cudaStreamNonBlocking));
         s.fit_concurrent = !(getenv("NPSWF_FIT_CONCURRENT") && atoi(getenv("NPSWF_FIT_CONCURRENT")) == 0);
         CR(cudaEventCreateWithFlags(&s.fit_fork, cudaEventDisableTiming));
+        CR(cudaEventCreateWithFlags(&s.last_use, cudaEventDisableTiming));
         for (int i = 0; i < 2; i++) CR(cudaEventCreateWithFlags(&s.chunk_join[i], cudaEventDisableTiming));
         for (int i = 0; i < 4; i++) {
             CR(cudaStreamCreateWithFlags(&s.fit_stream[i], cudaStreamNonBlocking));
@@ -1170,6 +1217,7 @@ void npswf_destroy(npswf_handle *h)
             if (s.fit_join[i]) cudaEventDestroy(s.fit_join[i]);
         }
         if (s.fit_fork) cudaEventDestroy(s.fit_fork);
+        if (s.last_use) cudaEventDestroy(s.last_use);
         for (int i = 0; i < 2; i++)
             if (s.chunk_join[i]) cudaEventDestroy(s.chunk_join[i]);
         for (cudaEvent_t e : s.prof_events) cudaEventDestroy(e);
@@ -1302,6 +1350,35 @@ int npswf_analyze_batch_flat(npswf_handle *h, int64_t n_events, const double *si
     return 0;
 }
 
+int npswf_analyze_batch_flat_i16(npswf_handle *h, int64_t n_events, const int16_t *counts, double lsb_mV, const int32_t *pres,
+                                 const double *corr_time_HMS, int32_t *wfnpulse, int64_t *pulse_offset, int32_t *pulse_count,
+                                 double *wftime_pool, double *wfampl_pool, int64_t pool_capacity, double *chi2, double *timewf,
+                                 double *amplwf, uint8_t *status, int64_t *n_pulses)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (n_events < 0 || pool_capacity < 0 || !(lsb_mV > 0) ||
+        (n_events > 0 && (!counts || !pres || !pulse_offset || !pulse_count || !wftime_pool || !wfampl_pool))) {
+        h->err = "npswf_analyze_batch_flat_i16: bad arguments";
+        return NPSWF_ERR_ARG;
+    }
+    if (n_pulses) *n_pulses = 0;
+    if (n_events == 0) return 0;
+    std::vector<int64_t> per_dev(h->slots.size(), 0);
+    HostIO io;
+    io.counts = counts; io.lsb = lsb_mV; io.pres = pres; io.corr = corr_time_HMS; io.wfnpulse = wfnpulse; io.chi2 = chi2;
+    io.timewf = timewf; io.amplwf = amplwf; io.status = status;
+    io.flat = true; io.pulse_offset = pulse_offset; io.pulse_count = pulse_count; io.pool_t = wftime_pool; io.pool_a = wfampl_pool;
+    io.pool_cap = pool_capacity; io.n_total = n_events; io.pulses_out = per_dev.data();
+    rc = for_each_slot_range(h, n_events, [&](int d, int64_t lo, int64_t hi) { return analyze_range(h, d, lo, hi, io); });
+    if (rc) return rc;
+    if (n_pulses)
+        for (int64_t v : per_dev) *n_pulses += v;
+    h->host_ctr.n_events += n_events;
+    h->host_ctr.n_block_waveforms += n_events * B;
+    return 0;
+}
+
 int npswf_analyze_batch_i16(npswf_handle *h, int64_t n_events, const int16_t *counts, double lsb_mV,
                             const int32_t *pres, const double *corr_time_HMS, int32_t *wfnpulse, double *wftime,
                             double *wfampl, double *chi2, double *timewf, double *amplwf, uint8_t *status)
@@ -1353,14 +1430,15 @@ int npswf_unpack_batch(npswf_handle *h, int64_t n_events, const double *samp, co
     if (n_events == 0) return 0;
     DevSlot &s = h->slots[0];
     CU_TRY(h, cudaSetDevice(s.device));
+    if ((rc = wait_last_use(h, s))) return rc;
     const size_t words = (size_t)(offsets[n_events] - offsets[0]);
-    double *d_s = nullptr, *d_sig = nullptr;
-    long long *d_o = nullptr;
-    int32_t *d_p = nullptr;
-    CU_TRY(h, cudaMalloc(&d_s, std::max<size_t>(words, 1) * sizeof(double)));
-    CU_TRY(h, cudaMalloc(&d_o, (size_t)(n_events + 1) * sizeof(long long)));
-    CU_TRY(h, cudaMalloc(&d_sig, (size_t)n_events * B * T * sizeof(double)));
-    CU_TRY(h, cudaMalloc(&d_p, (size_t)n_events * B * sizeof(int32_t)));
+    DevBuf<double> d_s, d_sig;
+    DevBuf<long long> d_o;
+    DevBuf<int32_t> d_p;
+    CU_TRY(h, d_s.alloc(words));
+    CU_TRY(h, d_o.alloc((size_t)(n_events + 1)));
+    CU_TRY(h, d_sig.alloc((size_t)n_events * B * T));
+    CU_TRY(h, d_p.alloc((size_t)n_events * B));
     CU_TRY(h, cudaMemcpy(d_s, samp + offsets[0], words * sizeof(double), cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(d_o, offsets, (size_t)(n_events + 1) * sizeof(long long), cudaMemcpyHostToDevice));
     unpack_kernel<<<(unsigned)std::min<int64_t>(n_events, 4 * s.sm_count), UNPACK_THREADS>>>(d_s, d_o, (long long)offsets[0],
@@ -1368,7 +1446,6 @@ int npswf_unpack_batch(npswf_handle *h, int64_t n_events, const double *samp, co
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaMemcpy(signal, d_sig, (size_t)n_events * B * T * sizeof(double), cudaMemcpyDeviceToHost));
     CU_TRY(h, cudaMemcpy(pres, d_p, (size_t)n_events * B * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    cudaFree(d_s); cudaFree(d_o); cudaFree(d_sig); cudaFree(d_p);
     return 0;
 }
 
@@ -1381,18 +1458,18 @@ int npswf_event_diagnostics_batch(npswf_handle *h, int64_t n_events, const doubl
     if (n_events == 0) return 0;
     DevSlot &s = h->slots[0];
     CU_TRY(h, cudaSetDevice(s.device));
-    double *d_sig = nullptr, *d_a = nullptr, *d_e = nullptr, *d_i = nullptr;
-    CU_TRY(h, cudaMalloc(&d_sig, (size_t)n_events * B * T * sizeof(double)));
-    CU_TRY(h, cudaMalloc(&d_a, (size_t)n_events * B * sizeof(double)));
-    CU_TRY(h, cudaMalloc(&d_e, (size_t)n_events * sizeof(double)));
-    CU_TRY(h, cudaMalloc(&d_i, (size_t)n_events * sizeof(double)));
+    if ((rc = wait_last_use(h, s))) return rc;
+    DevBuf<double> d_sig, d_a, d_e, d_i;
+    CU_TRY(h, d_sig.alloc((size_t)n_events * B * T));
+    CU_TRY(h, d_a.alloc((size_t)n_events * B));
+    CU_TRY(h, d_e.alloc((size_t)n_events));
+    CU_TRY(h, d_i.alloc((size_t)n_events));
     CU_TRY(h, cudaMemcpy(d_sig, signal, (size_t)n_events * B * T * sizeof(double), cudaMemcpyHostToDevice));
     diag_kernel<<<(unsigned)std::min<int64_t>(n_events, 8 * s.sm_count), DIAG_THREADS>>>(d_sig, n_events, d_a, d_e, d_i);
     CU_TRY(h, cudaGetLastError());
     if (ampl) CU_TRY(h, cudaMemcpy(ampl, d_a, (size_t)n_events * B * sizeof(double), cudaMemcpyDeviceToHost));
     if (enertot) CU_TRY(h, cudaMemcpy(enertot, d_e, (size_t)n_events * sizeof(double), cudaMemcpyDeviceToHost));
     if (integtot) CU_TRY(h, cudaMemcpy(integtot, d_i, (size_t)n_events * sizeof(double), cudaMemcpyDeviceToHost));
-    cudaFree(d_sig); cudaFree(d_a); cudaFree(d_e); cudaFree(d_i);
     return 0;
 }
 
@@ -1431,6 +1508,8 @@ int npswf_analyze_batch_device(npswf_handle *h, int32_t dev_slot, int64_t n_even
     DevSlot &s = h->slots[dev_slot];
     CU_TRY(h, cudaSetDevice(s.device));
     cudaStream_t st = stream ? (cudaStream_t)stream : s.own_stream;
+    // an earlier device-path call (possibly on another stream) may still be using the shared scratch and fit streams
+    if (s.last_use_valid) CU_TRY(h, cudaStreamWaitEvent(st, s.last_use, 0));
     // Chunks alternate between the two workspaces, each on its own internal stream forked from / joined to the
     // caller's stream: the front + search kernels of chunk k+1 fill the SMs the fit tails of chunk k leave idle.
     // With stage profiling on everything is serialised on the caller's stream so that the stage times are clean.
@@ -1460,6 +1539,8 @@ int npswf_analyze_batch_device(npswf_handle *h, int32_t dev_slot, int64_t n_even
             CU_TRY(h, cudaStreamWaitEvent(st, s.chunk_join[i], 0));
         }
     }
+    CU_TRY(h, cudaEventRecord(s.last_use, st));
+    s.last_use_valid = true;
     h->host_ctr.n_events += n_events;
     h->host_ctr.n_block_waveforms += n_events * B;
     return 0;
@@ -1505,6 +1586,7 @@ int npswf_find_pulses_mf_batch(npswf_handle *h, int64_t n_events, const double *
     if (n_events < 0 || (n_events > 0 && (!signal || !pres || !wfnpulse || !wftime || !wfampl))) return NPSWF_ERR_ARG;
     DevSlot &s = h->slots[0];
     CU_TRY(h, cudaSetDevice(s.device));
+    if ((rc = wait_last_use(h, s))) return rc;
     if ((rc = ensure_io(h, s))) return rc;
     Workspace &w = s.ws[0];
     cudaStream_t st = w.stream;
@@ -1534,6 +1616,7 @@ int npswf_pass_cluster_threshold_batch(npswf_handle *h, int64_t n_events, const 
     if (n_events < 0 || (n_events > 0 && (!signal || !pres || !ok))) return NPSWF_ERR_ARG;
     DevSlot &s = h->slots[0];
     CU_TRY(h, cudaSetDevice(s.device));
+    if ((rc = wait_last_use(h, s))) return rc;
     if ((rc = ensure_io(h, s))) return rc;
     Workspace &w = s.ws[0];
     cudaStream_t st = w.stream;
@@ -1559,6 +1642,7 @@ int npswf_matched_filter_batch(npswf_handle *h, int64_t n_events, const double *
     if (n_events < 0 || (n_events > 0 && (!signal || !pres || !mf))) return NPSWF_ERR_ARG;
     DevSlot &s = h->slots[0];
     CU_TRY(h, cudaSetDevice(s.device));
+    if ((rc = wait_last_use(h, s))) return rc;
     if ((rc = ensure_io(h, s))) return rc;
     Workspace &w = s.ws[0];
     cudaStream_t st = w.stream;
@@ -1585,6 +1669,7 @@ int npswf_fitwf_batch(npswf_handle *h, int64_t n_events, const double *signal, c
         return NPSWF_ERR_ARG;
     DevSlot &s = h->slots[0];
     CU_TRY(h, cudaSetDevice(s.device));
+    if ((rc = wait_last_use(h, s))) return rc;
     if ((rc = ensure_io(h, s))) return rc;
     Workspace &w = s.ws[0];
     cudaStream_t st = w.stream;
@@ -1624,14 +1709,15 @@ int npswf_tspectrum_debug(npswf_handle *h, int64_t n, const float *hist, int32_t
     if (n == 0) return 0;
     DevSlot &s = h->slots[0];
     CU_TRY(h, cudaSetDevice(s.device));
-    float *d_h = nullptr;
-    int32_t *d_n = nullptr;
-    double *d_p = nullptr, *d_s = nullptr, *d_d = nullptr;
-    CU_TRY(h, cudaMalloc(&d_h, (size_t)n * T * sizeof(float)));
-    CU_TRY(h, cudaMalloc(&d_n, (size_t)n * sizeof(int32_t)));
-    CU_TRY(h, cudaMalloc(&d_p, (size_t)n * MAXP * sizeof(double)));
-    CU_TRY(h, cudaMalloc(&d_s, (size_t)n * TS_S * sizeof(double)));
-    CU_TRY(h, cudaMalloc(&d_d, (size_t)n * T * sizeof(double)));
+    if ((rc = wait_last_use(h, s))) return rc;
+    DevBuf<float> d_h;
+    DevBuf<int32_t> d_n;
+    DevBuf<double> d_p, d_s, d_d;
+    CU_TRY(h, d_h.alloc((size_t)n * T));
+    CU_TRY(h, d_n.alloc((size_t)n));
+    CU_TRY(h, d_p.alloc((size_t)n * MAXP));
+    CU_TRY(h, d_s.alloc((size_t)n * TS_S));
+    CU_TRY(h, d_d.alloc((size_t)n * T));
     CU_TRY(h, cudaMemcpy(d_h, hist, (size_t)n * T * sizeof(float), cudaMemcpyHostToDevice));
     SearchArgs sa{};
     sa.hist = d_h; sa.n_items = n; sa.npeaks_out = d_n; sa.pos_out = d_p; sa.smoothed_out = d_s; sa.decon_out = d_d;
@@ -1641,7 +1727,6 @@ int npswf_tspectrum_debug(npswf_handle *h, int64_t n, const float *hist, int32_t
     if (pos_x) CU_TRY(h, cudaMemcpy(pos_x, d_p, (size_t)n * MAXP * sizeof(double), cudaMemcpyDeviceToHost));
     if (smoothed) CU_TRY(h, cudaMemcpy(smoothed, d_s, (size_t)n * TS_S * sizeof(double), cudaMemcpyDeviceToHost));
     if (decon) CU_TRY(h, cudaMemcpy(decon, d_d, (size_t)n * T * sizeof(double), cudaMemcpyDeviceToHost));
-    cudaFree(d_h); cudaFree(d_n); cudaFree(d_p); cudaFree(d_s); cudaFree(d_d);
     return 0;
 }
 
@@ -1652,14 +1737,14 @@ int npswf_debug_exp(npswf_handle *h, int64_t n, const double *x, double *y)
     if (n <= 0 || !x || !y) return NPSWF_ERR_ARG;
     DevSlot &s = h->slots[0];
     CU_TRY(h, cudaSetDevice(s.device));
-    double *dx = nullptr, *dy = nullptr;
-    CU_TRY(h, cudaMalloc(&dx, (size_t)n * 8));
-    CU_TRY(h, cudaMalloc(&dy, (size_t)n * 8));
+    if ((rc = wait_last_use(h, s))) return rc;
+    DevBuf<double> dx, dy;
+    CU_TRY(h, dx.alloc((size_t)n));
+    CU_TRY(h, dy.alloc((size_t)n));
     CU_TRY(h, cudaMemcpy(dx, x, (size_t)n * 8, cudaMemcpyHostToDevice));
     det_exp_debug_kernel<<<(unsigned)((n + 255) / 256), 256>>>(dx, dy, n);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaMemcpy(y, dy, (size_t)n * 8, cudaMemcpyDeviceToHost));
-    cudaFree(dx); cudaFree(dy);
     return 0;
 }
 
@@ -1682,8 +1767,9 @@ int npswf_debug_fp64_peak(npswf_handle *h, double *gflops)
     if (!gflops) return NPSWF_ERR_ARG;
     DevSlot &s = h->slots[0];
     CU_TRY(h, cudaSetDevice(s.device));
-    double *d = nullptr;
-    CU_TRY(h, cudaMalloc(&d, 8));
+    if ((rc = wait_last_use(h, s))) return rc;
+    DevBuf<double> d;
+    CU_TRY(h, d.alloc(1));
     cudaEvent_t e0, e1;
     CU_TRY(h, cudaEventCreate(&e0));
     CU_TRY(h, cudaEventCreate(&e1));
@@ -1696,7 +1782,7 @@ int npswf_debug_fp64_peak(npswf_handle *h, double *gflops)
     float ms = 0;
     CU_TRY(h, cudaEventElapsedTime(&ms, e0, e1));
     *gflops = 2.0 * 8.0 * (double)iters * 256.0 * blocks / (ms * 1e-3) / 1e9;
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
     return 0;
 }
 
@@ -1707,8 +1793,9 @@ int npswf_debug_exact_ops(npswf_handle *h, int64_t n_trials, uint64_t seed, uint
     if (n_trials <= 0 || !mismatch) return NPSWF_ERR_ARG;
     DevSlot &s = h->slots[0];
     CU_TRY(h, cudaSetDevice(s.device));
-    unsigned long long *d = nullptr;
-    CU_TRY(h, cudaMalloc(&d, 16));
+    if ((rc = wait_last_use(h, s))) return rc;
+    DevBuf<unsigned long long> d;
+    CU_TRY(h, d.alloc(2));
     CU_TRY(h, cudaMemset(d, 0, 16));
     const int threads = 256, blocks = s.sm_count * 8;
     const int per_thread = (int)std::min<int64_t>(1 << 20, (n_trials + (int64_t)threads * blocks - 1) / ((int64_t)threads * blocks));
@@ -1716,7 +1803,6 @@ int npswf_debug_exact_ops(npswf_handle *h, int64_t n_trials, uint64_t seed, uint
     CU_TRY(h, cudaGetLastError());
     unsigned long long out[2] = {0, 0};
     CU_TRY(h, cudaMemcpy(out, d, 16, cudaMemcpyDeviceToHost));
-    cudaFree(d);
     mismatch[0] = out[0];
     mismatch[1] = out[1];
     return 0;

@@ -476,15 +476,17 @@ extern "C" int oracle_unpack_event(const double *samp, int64_t n_words, double *
     for (int i = 0; i < B * T; i++) signal[i] = 0.;          // T2:851
     for (int i = 0; i < B; i++) { pres[i] = 0; if (minsignal) minsignal[i] = 1.0e6; }   // T2:548, 550
     if (n_words > Ndata) return 0;                 // T2:830-836: the event is not processed
+    // Int_t bloc, nsamp (T2:553): the doubles are truncated on assignment; NaN / out-of-range give INT_MIN on x86-64
+    auto to_int_t = [](double v) { return (v > -2147483649.0 && v < 2147483648.0) ? (int)v : (int)0x80000000; };
     int64_t ns = 0;
     int nrec = 0;
     while (ns + 1 < n_words) {                     // T2:855 (a header is two words)
-        double bloc = samp[ns]; ns++;
-        const int nsamp = (int)samp[ns]; ns++;
+        int bloc = to_int_t(samp[ns]); ns++;
+        const int nsamp = to_int_t(samp[ns]); ns++;
         if (bloc == 2000) bloc = 1080;             // T2:862-865
         if (bloc == 2001) bloc = 1081;
         if (bloc < 0 || bloc > nslots - 0.5) break;   // T2:867-872
-        const int b = (int)bloc;
+        const int b = bloc;
         if (b < B) pres[b] = 1;                    // T2:877 (bounded, see above)
         for (int it = 0; it < nsamp; it++) {       // T2:879-887
             if (b < B && it < T && ns < n_words) {

@@ -385,7 +385,7 @@ def _malformed_streams(rng):
     """Packed streams exercising every branch of T2:855-889."""
     x = np.arange(110.0)
     def rec(slot, n, vals=None):
-        v = rng.normal(0, 1, n) if vals is None else np.asarray(vals, float)
+        v = rng.normal(0, 1, int(n)) if vals is None else np.asarray(vals, float)
         return np.concatenate([[slot, n], v])
     evs = []
     evs.append(np.concatenate([rec(3, 110), rec(2000, 110), rec(1079, 110), rec(2001, 110), rec(0, 110)]))      # scintillators
@@ -399,6 +399,12 @@ def _malformed_streams(rng):
     evs.append(np.zeros(0))                                                                                      # empty
     evs.append(np.concatenate([rec(s, 110) for s in range(1104)] + [rec(2000, 110)]))                            # > 1104*112 words: skipped
     evs.append(np.concatenate([rec(s, 110) for s in rng.permutation(1080)]))                                     # full event
+    # Int_t truncation of the header words (T2:553, 857-859): -0.5 is slot 0, 2000.7 is the scintillator slot 2000
+    evs.append(np.concatenate([rec(-0.5, 110), rec(2000.7, 110), rec(17.9, 110)]))
+    evs.append(np.concatenate([rec(40, 110), rec(np.nan, 110), rec(41, 110)]))                                   # NaN slot ends the event
+    evs.append(np.concatenate([rec(42, np.nan, []), rec(43, 3e9, []), rec(44, -7, []), rec(45, 110)]))           # nsamp not a count: no samples
+    evs.append(np.concatenate([rec(s % 1080, 0, []) for s in range(2500)] + [rec(33, 110), rec(34, 5)]))         # > 1104 records
+    evs.append(np.concatenate([rec(7, 20, x[:20] + 1)] + [rec(s % 50, 1, [s]) for s in range(1300)] + [rec(7, 10, -x[:10] - 1)]))  # repeats across rounds
     offs = np.concatenate([[0], np.cumsum([e.size for e in evs])]).astype(np.int64)
     return np.concatenate(evs), offs
 
@@ -417,6 +423,9 @@ def test_unpack_exact(gpu, events):
         assert np.array_equal(pres[e], rp), e
         assert np.array_equal(sig[e], rs), e
     assert pres[9].sum() == 0 and pres[10].sum() == 1080 and pres[1].sum() == 1 and pres[6].sum() == 1
+    assert pres[11, 0] == 1 and pres[11, 17] == 1 and pres[11].sum() == 2          # -0.5 -> slot 0, 2000.7 -> scintillator, 17.9 -> 17
+    assert pres[12].sum() == 1 and pres[13, 45] == 1 and pres[14, 33] == 1 and pres[14, 34] == 1
+    assert sig[15, 7, 0] == -1.0 and sig[15, 7, 10] == 11.0                         # the later record of slot 7 wins, 10 samples only
 
 
 def test_analyze_packed_equals_analyze(gpu, events):
@@ -672,3 +681,82 @@ def test_full_size_configs_by_properties(pkg, calib):
             assert c["n_peak_buffer_full"] > 0 and c["n_fallback"] + c["n_fit_ok_retry"] > 0
         del sig, pres, corr, oa, ob
         torch.cuda.empty_cache()
+
+
+def test_flat_i16_entry_point(gpu, events):
+    """npswf_analyze_batch_flat_i16 (int16 counts in, reference packing out) equals the binary64 flat call."""
+    ev = events[2]
+    a = gpu.analyze_flat(ev["signal"], ev["pres"], ev["corr_time_HMS"])
+    b = gpu.analyze_flat_i16(ev["counts"], synth.LSB, ev["pres"], ev["corr_time_HMS"])
+    assert a["n_pulses"] == b["n_pulses"] > 0
+    n = a["n_pulses"]
+    for k in ("wfnpulse", "pulse_offset", "pulse_count", "chi2", "timewf", "amplwf", "status"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["wftime_pool"][:n], b["wftime_pool"][:n]) and np.array_equal(a["wfampl_pool"][:n], b["wfampl_pool"][:n])
+
+
+def test_device_calls_on_different_streams_are_ordered(pkg, calib, spline):
+    """Two device-path calls enqueued back to back on DIFFERENT streams share the handle's scratch, job lists and fit
+    streams: the second one orders itself behind the first (last-use event), so both give what they give alone; a
+    host-buffer call right after them waits for them too."""
+    import torch
+    E = 400
+    ev = [synth.generate_host(synth.config_params(2, absent_frac=0.02), spline, calib, 95_000 + 1000 * i, E, n_threads=8) for i in range(2)]
+    h = pkg.NpsWf(calib)
+    alone = [_device_analyze(h, ev[i], E) for i in range(2)]
+    dev = torch.device("cuda:0")
+    ins, outs, streams = [], [], [torch.cuda.Stream(), torch.cuda.Stream()]
+    for i in range(2):
+        ins.append((torch.from_numpy(ev[i]["signal"]).to(dev), torch.from_numpy(ev[i]["pres"]).to(dev),
+                    torch.from_numpy(ev[i]["corr_time_HMS"]).to(dev)))
+        outs.append(dict(wfnpulse=torch.empty((E, 1080), dtype=torch.int32, device=dev),
+                         wftime=torch.empty((E, 1080, 12), dtype=torch.float64, device=dev),
+                         wfampl=torch.empty((E, 1080, 12), dtype=torch.float64, device=dev),
+                         chi2=torch.empty((E, 1080), dtype=torch.float64, device=dev),
+                         timewf=torch.empty((E, 1080), dtype=torch.float64, device=dev),
+                         amplwf=torch.empty((E, 1080), dtype=torch.float64, device=dev),
+                         status=torch.empty((E, 1080), dtype=torch.uint8, device=dev)))
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for i in range(2):
+            o = outs[i]
+            h.analyze_device(E, ins[i][0].data_ptr(), ins[i][1].data_ptr(), ins[i][2].data_ptr(), o["wfnpulse"].data_ptr(),
+                             o["wftime"].data_ptr(), o["wfampl"].data_ptr(), o["chi2"].data_ptr(), o["timewf"].data_ptr(),
+                             o["amplwf"].data_ptr(), o["status"].data_ptr(), stream=streams[i].cuda_stream)
+        host = h.analyze(ev[0]["signal"][:50], ev[0]["pres"][:50], ev[0]["corr_time_HMS"][:50])   # no explicit sync before it
+        torch.cuda.synchronize()
+        for i in range(2):
+            for k in alone[i]:
+                assert np.array_equal(outs[i][k].cpu().numpy(), alone[i][k]), (rep, i, k)
+        for k in host:
+            assert np.array_equal(host[k], alone[0][k][:50]), (rep, k)
+
+
+def test_non_finite_samples_end_as_fallback(pkg, gpu, orc, calib, events):
+    """A NaN / Inf sample inside the fit window makes chi2 not a number: no descent step exists, and the fit must end
+    as a failed fit (TSpectrum values, chi2 = -100, T2:774-791) -- not as a 'converged' fit with a NaN chi2.  Driven
+    through the stage-level Fitwf entry point with the seeds of the clean traces."""
+    ev = events[1]
+    sig0, pres, corr = ev["signal"][:1], ev["pres"][:1], ev["corr_time_HMS"][:1]
+    n, t, a = gpu.FindPulsesMF(sig0, pres)
+    ok = gpu.PassClusterThreshold(sig0, pres)
+    blocks = np.flatnonzero(ok[0] & (n[0] > 0))[:40]
+    assert blocks.size >= 20
+    sig = sig0.copy()
+    for j, b in enumerate(blocks):
+        sig[0, b, 60 + j % 30] = np.nan if j % 2 == 0 else np.inf
+    mask = np.zeros((1, 1080), np.uint8)
+    mask[0, blocks] = 1
+    r = gpu.Fitwf(sig, corr, mask, n, t, a)        # FAST (LM) mode: a failed fit
+    for b in blocks:
+        assert (r["status"][0, b] & 28) == 16 and r["chi2"][0, b] == -100.0, (b, r["status"][0, b], r["chi2"][0, b])
+        assert np.array_equal(r["wfampl"][0, b, :n[0, b]], a[0, b, :n[0, b]])
+    # MIGRAD mode follows the Migrad restatement wherever it goes (a NaN EDM ends VariableMetricBuilder with the
+    # current state): verdict and values equal the oracle's, NaN for NaN
+    hm = pkg.NpsWf(calib, fit_mode=pkg.FIT_MIGRAD)
+    rm = hm.Fitwf(sig, corr, mask, n, t, a)
+    for b in blocks[:12]:
+        o = orc.fitwf(b, sig[0], n[0, b], t[0, b], a[0, b], corr[0])
+        assert (rm["status"][0, b] & 28) == o["status"], (b, rm["status"][0, b], o["status"])
+        assert np.array_equal(rm["chi2"][0, b], o["chi2"], equal_nan=True)
+        assert np.array_equal(rm["wftime"][0, b, :n[0, b]], o["wftime"][:n[0, b]], equal_nan=True)

@@ -1,0 +1,10 @@
+#!/bin/bash
+# A/B builds of the Migrad translation unit: tools/ab_build_migrad.sh <tag> [nvcc -D flags...] -> nps-waveform-analysis_b200/lib/libnpswf_<tag>.so
+# (same ABI, the other objects of the regular build are reused; select with NPSWF_LIB=...)
+set -e
+cd "$(dirname "$0")/.."
+tag=$1; shift
+P=nps-waveform-analysis_b200
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -fmad=false "$@" -c -o $P/lib/obj/npswf_migrad_$tag.o $P/csrc/npswf_migrad.cu
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $P/lib/libnpswf_$tag.so $P/lib/obj/npswf_api.o $P/lib/obj/npswf_migrad_$tag.o $P/lib/obj/host_pack.o
+echo built $P/lib/libnpswf_$tag.so
