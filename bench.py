@@ -99,7 +99,7 @@ def run_reference(args, rank, world):
     orc = oracle.Oracle(cal)
     spl = orc.spline_coeffs()
     threads = os.cpu_count() or 1
-    n_ev = args.ref_events
+    n_ev = args.ref_events if args.ref_events > 0 else max(96, 6 * threads)   # >= 6 events per thread: the pool stays loaded
     p = synth.config_params(2)
     times, fitted = [], 0
     for s in range(args.warmup + args.steps):
@@ -118,6 +118,11 @@ def run_reference(args, rank, world):
     t0 = time.perf_counter()
     rf = orc_f.analyze_batch(ev["signal"], ev["pres"], ev["corr_time_HMS"], n_threads=threads)
     faithful = float(((rf["status"] & 28) > 0).sum()) / (time.perf_counter() - t0)
+    # BASELINE configs[0]: single pulse per block with EnableImplicitMT(4) (T2:313, README:33): 4 threads, bounded sample
+    ev0 = synth.generate_host(synth.config_params(1), spl, cal, 20_000_000, 48, n_threads=threads)
+    t0 = time.perf_counter()
+    r0 = orc.analyze_batch(ev0["signal"], ev0["pres"], ev0["corr_time_HMS"], n_threads=4)
+    cfg0 = float(((r0["status"] & 28) > 0).sum()) / (time.perf_counter() - t0)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, len(times)), "higher_is_better": True,
@@ -128,7 +133,9 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "%d events/step x %d steps of the same workload" % (n_ev, args.steps),
                          "faithful_cost_mode": {"value": faithful, "unit": UNIT,
-                                                "sample": "%d events, spline rebuilt per fit + search mutex" % n_ev}},
+                                                "sample": "%d events, spline rebuilt per fit + search mutex" % n_ev},
+                         "config0_4_threads": {"value": cfg0, "unit": UNIT, "cores": 4,
+                                               "sample": "BASELINE configs[0]: 48 of its 1 000 single-pulse events, 4 threads (EnableImplicitMT(4))"}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -144,9 +151,10 @@ def main():
     ap.add_argument("--batch-events", type=int, default=9472,
                     help="events per step per GPU: one npswf_analyze_batch_device call, which the library cuts into two chunks of 4 736")
     ap.add_argument("--e2e-events", type=int, default=4736, help="events per end-to-end step per GPU")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--migrad-steps", type=int, default=2, help="steps of the MIGRAD-fit-mode leg (0 = skip)")
     ap.add_argument("--stage-steps", type=int, default=4, help="steps of the serialised stage-profiling pass")
-    ap.add_argument("--ref-events", type=int, default=24, help="--impl reference: events per step")
+    ap.add_argument("--ref-events", type=int, default=0, help="--impl reference: events per step (0 = 6 per host thread, at least 96)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -260,9 +268,29 @@ def main():
 
     # ---- end to end through npswf_analyze_batch: pinned host buffers, H2D + D2H inside the timed region
     e2e = None
+    migrad = None
+
+    def e2e_leg(hh, call, steps):
+        """One warm-up call, then `steps` synchronous calls timed on the host clock between barriers; max over ranks."""
+        call()
+        hh.reset_counters()
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            call()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        c = hh.counters()
+        te = torch.tensor([dt], dtype=torch.float64, device=dev)
+        ce = torch.tensor([c["n_fit_attempted"]], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ce, op=dist.ReduceOp.SUM)
+        return float(ce.item()) / float(te.item()), 1e3 * float(te.item()) / steps
+
     if not args.no_e2e:
-        # per-rank pinned host buffers are ~1.4 MB per event: keep the node's total modest when many ranks share the host
-        Ee = args.e2e_events if world <= 2 else max(1184, args.e2e_events // (world // 2))
+        Ee = args.e2e_events      # the same step at every N (weak scaling): ~6.8 GB of pinned host memory per rank
         hs = pkg.pinned_empty((Ee, NB, NT), np.float64)
         hp = pkg.pinned_empty((Ee, NB), np.int32)
         hc = pkg.pinned_empty((Ee,), np.float64)
@@ -273,104 +301,109 @@ def main():
             hp[o0:o0 + n] = b[1][:n].cpu().numpy()
             hc[o0:o0 + n] = b[2][:n].cpu().numpy()
         ho = h.alloc_outputs(Ee, pinned=True)
-        h.analyze(hs, hp, hc, out=ho)          # warm-up (allocates the staging buffers)
-        h.analyze(hs, hp, hc, out=ho)
-        h.reset_counters()
-        ps0 = h.host_packing_stats()
-        barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            h.analyze(hs, hp, hc, out=ho)      # synchronous: returns when every output is in host memory
-        torch.cuda.synchronize()
-        dt_e2e = time.perf_counter() - t0
-        c2 = h.counters()
-        ps1 = h.host_packing_stats()
-        packed_in = (ps1["packed_input_bytes"] - ps0["packed_input_bytes"]) // args.e2e_steps
-        te = torch.tensor([dt_e2e], dtype=torch.float64, device=dev)
-        ce = torch.tensor([c2["n_fit_attempted"]], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            dist.all_reduce(ce, op=dist.ReduceOp.SUM)
         host_in = hs.nbytes + hp.nbytes + hc.nbytes
-        h2d = host_in - (packed_in * 3) // 4        # what crossed PCIe: the packed part of the traces is a quarter of its size
         d2h = sum(v.nbytes for v in ho.values())
-        e2e = {"value": float(ce.item()) / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+        # what the host link gives every rank when all ranks upload at once: 1 GiB of the pinned trace buffer, raw
+        probe_t = torch.empty((1 << 27,), dtype=torch.float64, device=dev)
+        src = torch.from_numpy(np.asarray(hs).reshape(-1)[:1 << 27])
+        probe_t.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        barrier()
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record(stream)
+        for _ in range(3):
+            probe_t.copy_(src, non_blocking=True)
+        pe1.record(stream)
+        torch.cuda.synchronize()
+        h2d_gbs = torch.tensor([3 * (1 << 30) / (pe0.elapsed_time(pe1) * 1e-3) / 1e9], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(h2d_gbs, op=dist.ReduceOp.MIN)
+        del probe_t, src
+        h.analyze(hs, hp, hc, out=ho)          # allocates the staging buffers
+        ps0 = h.host_packing_stats()
+        v, ms = e2e_leg(h, lambda: h.analyze(hs, hp, hc, out=ho), args.e2e_steps)
+        ps1 = h.host_packing_stats()
+        packed_in = (ps1["packed_input_bytes"] - ps0["packed_input_bytes"]) // (args.e2e_steps + 1)
+        h2d = host_in - (packed_in * 3) // 4        # what crossed PCIe: the packed part of the traces is a quarter of its size
+        up_rate, bound_cpus = h.host_upload_rate()
+        e2e = {"value": v, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "events_per_step_per_gpu": Ee, "steps": args.e2e_steps,
                "host_input_bytes_per_step": int(host_in),
                "input": "f64 [E][1080][110] (the reference's Double_t layout), pinned host memory",
                "transport": "library default: host threads rewrite lattice traces as int16 counts when that reproduces every "
                             "double (lossless, checked per sample), raw doubles otherwise; %.0f %% of the trace bytes packed at "
                             "%.1f GB/s" % (100.0 * packed_in / max(1, hs.nbytes), ps1["pack_gb_per_s"]),
-               "ms_per_step": 1e3 * float(te.item()) / args.e2e_steps}
+               "ms_per_step": ms,
+               "host_link": {"h2d_gbs_per_rank_all_ranks_uploading": float(h2d_gbs.item()),
+                             "note": "plain pinned H2D copy of 1 GiB, all ranks at once, slowest rank",
+                             "library_measured_raw_upload_gbs": up_rate, "numa_bound_cpus": bound_cpus}}
         # the same call with the packing off: every trace crosses PCIe as binary64
         h.set_host_packing(0)
-        h.analyze(hs, hp, hc, out=ho)
-        h.reset_counters()
-        barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            h.analyze(hs, hp, hc, out=ho)
-        torch.cuda.synchronize()
-        dtr = time.perf_counter() - t0
-        cr = h.counters()
+        v, ms = e2e_leg(h, lambda: h.analyze(hs, hp, hc, out=ho), max(2, args.e2e_steps // 3))
         h.set_host_packing(1)
-        te = torch.tensor([dtr], dtype=torch.float64, device=dev)
-        ce = torch.tensor([cr["n_fit_attempted"]], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            dist.all_reduce(ce, op=dist.ReduceOp.SUM)
-        e2e["f64_raw_transport"] = {"value": float(ce.item()) / float(te.item()), "unit": UNIT,
-                                    "h2d_bytes_per_step": int(host_in), "d2h_bytes_per_step": int(d2h),
-                                    "ms_per_step": 1e3 * float(te.item()) / args.e2e_steps,
-                                    "input": "same call, npswf_set_host_packing(0): PCIe-bound"}
+        e2e["f64_raw_transport"] = {"value": v, "unit": UNIT, "h2d_bytes_per_step": int(host_in), "d2h_bytes_per_step": int(d2h),
+                                    "ms_per_step": ms, "input": "same call, npswf_set_host_packing(0): PCIe-bound"}
         # the same analysis through npswf_analyze_batch_flat: wfampl / wftime come back in the reference's truncated
         # layout (T2:1289-1296), packed on the device -- a fraction of the D2H bytes, no flatten pass on the host
         hf = h.alloc_flat_outputs(Ee, Ee * NB * 4, pinned=True)
-        h.analyze_flat(hs, hp, hc, out=hf)
-        h.reset_counters()
-        barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            h.analyze_flat(hs, hp, hc, out=hf)
-        torch.cuda.synchronize()
-        dtf = time.perf_counter() - t0
-        cf = h.counters()
-        te = torch.tensor([dtf], dtype=torch.float64, device=dev)
-        ce = torch.tensor([cf["n_fit_attempted"]], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            dist.all_reduce(ce, op=dist.ReduceOp.SUM)
+        v, ms = e2e_leg(h, lambda: h.analyze_flat(hs, hp, hc, out=hf), max(2, args.e2e_steps // 3))
         fixed = sum(hf[k].nbytes for k in ("wfnpulse", "chi2", "timewf", "amplwf", "status"))
-        e2e["flat_outputs"] = {"value": float(ce.item()) / float(te.item()), "unit": UNIT,
-                               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(fixed + 16 * hf["n_pulses"] + 4 * Ee),
-                               "ms_per_step": 1e3 * float(te.item()) / args.e2e_steps,
+        d2h_flat = int(fixed + 16 * hf["n_pulses"] + 12 * Ee)
+        e2e["flat_outputs"] = {"value": v, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h_flat,
+                               "ms_per_step": ms,
                                "input": "same f64 host input; npswf_analyze_batch_flat (pulses packed on the device)"}
-        del hf
-        # the same call with the int16 ADC-count ABI (exact on the 1000/4096 mV lattice): 4x less PCIe traffic in
+        # the int16 ADC-count ABI (exact on the 1000/4096 mV lattice): 4x less PCIe traffic in
         hk = pkg.pinned_empty((Ee, NB, NT), np.int16)
         hk[...] = np.rint(hs / synth.LSB).astype(np.int16)
-        h.analyze_i16(hk, synth.LSB, hp, hc, out=ho)
-        h.reset_counters()
+        v, ms = e2e_leg(h, lambda: h.analyze_i16(hk, synth.LSB, hp, hc, out=ho), max(2, args.e2e_steps // 3))
+        h2d_i16 = int(hk.nbytes + hp.nbytes + hc.nbytes)
+        e2e["i16_abi"] = {"value": v, "unit": UNIT, "h2d_bytes_per_step": h2d_i16, "d2h_bytes_per_step": int(d2h), "ms_per_step": ms,
+                          "input": "int16 ADC counts [E][1080][110] + lsb (npswf_analyze_batch_i16), pinned host memory"}
+        # the multi-GPU transport: int16 counts in, the reference's packing out (npswf_analyze_batch_flat_i16)
+        v, ms = e2e_leg(h, lambda: h.analyze_flat_i16(hk, synth.LSB, hp, hc, out=hf), args.e2e_steps)
+        e2e["i16_flat"] = {"value": v, "unit": UNIT, "h2d_bytes_per_step": h2d_i16, "d2h_bytes_per_step": d2h_flat, "ms_per_step": ms,
+                           "bytes_per_block_waveform": (h2d_i16 + d2h_flat) / float(Ee * NB),
+                           "input": "npswf_analyze_batch_flat_i16: int16 counts in, pulses packed on the device out"}
+
+    # ---- the MIGRAD fit mode (the reference's own minimiser on the device; outputs bit-identical to the oracle): the
+    # same resident batches and the same host call, fewer steps (a step takes ~10x longer)
+    if args.migrad_steps > 0:
+        hm = pkg.NpsWf(cal, devices=[local_rank], fit_mode=pkg.FIT_MIGRAD)
+
+        def mstep(i):
+            sig, pres, corr = bufs[i % n_buf]
+            hm.analyze_device(E, sig.data_ptr(), pres.data_ptr(), corr.data_ptr(), out["wfnpulse"].data_ptr(),
+                              out["wftime"].data_ptr(), out["wfampl"].data_ptr(), out["chi2"].data_ptr(),
+                              out["timewf"].data_ptr(), out["amplwf"].data_ptr(), out["status"].data_ptr(), stream=st)
+        mstep(0)
+        hm.sync_device(stream=st)
+        hm.reset_counters()
         barrier()
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            h.analyze_i16(hk, synth.LSB, hp, hc, out=ho)
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record(stream)
+        for i in range(args.migrad_steps):
+            mstep(1 + i)
+        m1.record(stream)
         torch.cuda.synchronize()
-        dt16 = time.perf_counter() - t0
-        c3 = h.counters()
-        te = torch.tensor([dt16], dtype=torch.float64, device=dev)
-        ce = torch.tensor([c3["n_fit_attempted"]], dtype=torch.int64, device=dev)
+        hm.sync_device(stream=st)
+        mc = hm.counters()
+        tm = torch.tensor([m0.elapsed_time(m1)], dtype=torch.float64, device=dev)
+        cm = torch.tensor([mc["n_fit_attempted"], mc["n_fit_evals"], mc["n_fit_ok_retry"], mc["n_fallback"]], dtype=torch.int64, device=dev)
         if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            dist.all_reduce(ce, op=dist.ReduceOp.SUM)
-        e2e["i16_abi"] = {"value": float(ce.item()) / float(te.item()), "unit": UNIT,
-                          "h2d_bytes_per_step": int(hk.nbytes + hp.nbytes + hc.nbytes), "d2h_bytes_per_step": int(d2h),
-                          "ms_per_step": 1e3 * float(te.item()) / args.e2e_steps,
-                          "input": "int16 ADC counts [E][1080][110] + lsb (npswf_analyze_batch_i16), pinned host memory"}
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cm, op=dist.ReduceOp.SUM)
+        migrad = {"value": float(cm[0].item()) / (float(tm.item()) * 1e-3), "unit": UNIT, "steps": args.migrad_steps,
+                  "ms_per_step": float(tm.item()) / args.migrad_steps,
+                  "chi2_evaluations_per_fit": float(cm[1].item()) / max(1.0, float(cm[0].item())),
+                  "retry_ok": int(cm[2].item()), "fallback": int(cm[3].item()),
+                  "note": "fit_mode = NPSWF_FIT_MIGRAD: Minuit2-Migrad re-implemented on the device (numerical gradients, strategy "
+                          "1 -> 2), every output bit-identical to the CPU oracle (tests/test_gpu_migrad.py); same resident batches"}
+        if not args.no_e2e:
+            v, ms = e2e_leg(hm, lambda: hm.analyze(hs, hp, hc, out=ho), 2)
+            migrad["e2e"] = {"value": v, "unit": UNIT, "ms_per_step": ms, "h2d_bytes_per_step": e2e["h2d_bytes_per_step"],
+                             "d2h_bytes_per_step": e2e["d2h_bytes_per_step"], "input": "same f64 host call as e2e"}
+        del hm
 
     if rank != 0:
         if world > 1:
@@ -466,7 +499,7 @@ def main():
                    "fitted_fraction": fitted / max(1, blocks), "mean_pulses_per_fit": n_mean,
                    "fit_iterations_mean": iters / max(1, fitted), "fallback": n_fb, "retry_ok": n_retry,
                    "l2": "inputs larger than L2: %.2f GB of traces per step, two resident batches alternated" % (E * NB * NT * 8 / 1e9)},
-        "clocks": clocks, "e2e": e2e,
+        "clocks": clocks, "e2e": e2e, "fit_mode": "NPSWF_FIT_FAST (Levenberg-Marquardt, library default)", "fit_mode_migrad": migrad,
         # front, search, compact and 18 fit kernels per chunk; chunks per step as counted by the library in the stage pass
         "gpu_launches": int(args.steps * (chunks // max(1, args.stage_steps)) * 21),
         "roofline": roofline, "stages": stage_rows,

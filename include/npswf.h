@@ -164,6 +164,12 @@ int npswf_debug_pack_counts(const double *x, int64_t n, double lsb_mV, int32_t n
 int npswf_host_packing_stats(const npswf_handle *h, int64_t *packed_chunks, int64_t *raw_chunks, double *pack_gb_per_s,
                              int64_t *packed_input_bytes);
 
+/* Measured rate of the raw binary64 uploads out of the caller's pinned buffers (CUDA events around the raw part of a
+ * chunk, running mean over the devices; 48 until something was measured), and the number of host cores the packer
+ * threads / staging buffers are confined to (the cores of each GPU's NUMA node, from sysfs; 0 = topology not visible
+ * or NPSWF_NUMA_BIND=0).  Either pointer may be NULL. */
+int npswf_host_upload_rate(const npswf_handle *h, double *raw_gb_per_s, int32_t *numa_bound_cpus);
+
 /* Same, all pointers DEVICE memory on the handle's device `dev_slot` (index into cfg.devices),
  * enqueued on `stream` (a cudaStream_t; NULL = the library's own stream) and NOT synchronised. */
 int npswf_analyze_batch_device(npswf_handle *h, int32_t dev_slot, int64_t n_events, const double *d_signal,

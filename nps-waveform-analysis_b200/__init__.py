@@ -58,7 +58,7 @@ EXPORTS = [
     "npswf_device_timeref", "npswf_flatten_event", "npswf_debug_exp", "npswf_debug_exact_ops", "npswf_debug_fp64_peak", "npswf_unpack_batch", "npswf_analyze_batch_packed",
     "npswf_event_diagnostics_batch", "npswf_event_diagnostics_device", "npswf_set_profiling",
     "npswf_get_stage_times", "npswf_set_host_packing", "npswf_host_packing_stats", "npswf_debug_pack_counts", "npswf_analyze_batch_flat",
-    "npswf_analyze_batch_flat_i16",
+    "npswf_analyze_batch_flat_i16", "npswf_host_upload_rate",
 ]
 
 _lib = None
@@ -244,6 +244,12 @@ class NpsWf:
         a, b, r, n = C.c_int64(), C.c_int64(), C.c_double(), C.c_int64()
         self._check(lib().npswf_host_packing_stats(self.h, C.byref(a), C.byref(b), C.byref(r), C.byref(n)))
         return dict(packed_chunks=a.value, raw_chunks=b.value, pack_gb_per_s=r.value, packed_input_bytes=n.value)
+
+    def host_upload_rate(self):
+        """(measured GB/s of the raw binary64 uploads, host cores the transport threads are bound to)."""
+        r, c = C.c_double(), C.c_int32()
+        self._check(lib().npswf_host_upload_rate(self.h, C.byref(r), C.byref(c)))
+        return r.value, c.value
 
     # ---- analyze(event) over a batch (T2:540-1300 hot path)
     @staticmethod

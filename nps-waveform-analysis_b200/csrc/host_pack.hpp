@@ -20,8 +20,21 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#include <sched.h>
+#include <pthread.h>
 
 namespace npswf {
+
+// Restrict the calling thread to `cpus` (the cores of a GPU's NUMA node); an empty list is a no-op.
+inline void bind_this_thread(const std::vector<int> &cpus)
+{
+    if (cpus.empty()) return;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    for (int c : cpus)
+        if (c >= 0 && c < CPU_SETSIZE) CPU_SET(c, &set);
+    (void)pthread_setaffinity_np(pthread_self(), sizeof set, &set);
+}
 
 // counts[i] = round(x[i] / lsb) for i in [0, n); returns true iff every sample is reproduced bit for bit.
 // (host_pack.cpp: AVX2 when the CPU has it, portable C++ otherwise)
@@ -30,9 +43,10 @@ bool pack_counts_range(const double *x, int16_t *out, size_t n, double lsb, doub
 // Persistent fork-join pool: pack() splits one chunk over the workers and the calling thread.
 class PackPool {
 public:
-    explicit PackPool(int n_threads) : n_(n_threads < 1 ? 1 : n_threads)
+    // cpus: the cores the workers are confined to (those next to the GPU the packed chunks go to); empty = anywhere
+    explicit PackPool(int n_threads, std::vector<int> cpus = {}) : n_(n_threads < 1 ? 1 : n_threads), cpus_(std::move(cpus))
     {
-        for (int t = 1; t < n_; t++) workers_.emplace_back([this, t] { loop(t); });
+        for (int t = 1; t < n_; t++) workers_.emplace_back([this, t] { bind_this_thread(cpus_); loop(t); });
     }
     ~PackPool()
     {
@@ -96,6 +110,7 @@ private:
     }
 
     const int n_;
+    const std::vector<int> cpus_;
     std::vector<std::thread> workers_;
     std::mutex mu_;
     std::condition_variable cv_, done_cv_;

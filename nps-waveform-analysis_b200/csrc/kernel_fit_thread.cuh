@@ -272,7 +272,7 @@ fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
                         const int c = 32 * c4 + lane;
                         if (c >= MFSTART && c < MFEND && its[k] >= 0) {
                             const float yf = (float)v[k][c4];
-                            exact = exact && ((double)yf == v[k][c4]);
+                            exact = exact && ((double)yf == v[k][c4]) && (fabsf(yf) <= 3.0e38f);   // NaN fails the first test, +-Inf the second
                             ywwarp[(c - MFSTART) * FT_LD + ls[k]] = make_float2(yf, inv_err_f32(v[k][c4]));
                         }
                     }
@@ -332,10 +332,7 @@ fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
             } else {
                 lambda = fmax(lambda * 10, 1e-6);
                 rejects++;
-                if (rejects >= 30) {   // no descent step left; a chi2 that is not a number goes through the retry policy of the sub-warp kernel
-                    if (isfinite(cur.c2)) { finished = true; iters++; }
-                    else handoff = true;
-                }
+                if (rejects >= 30) { finished = true; iters++; }  // no descent step left (chi2 is finite here: a trace with a NaN / Inf sample never stays in this kernel)
             }
             bool restart = false;
             if (!finished && !handoff && tries >= max_tries) { handoff = true; restart = N >= 4; }

@@ -84,6 +84,7 @@ struct DevSlot {
     int occ_migrad_thread[4] = {0, 4, 4, 4};   // fit_migrad_thread_kernel<1, 2, 3>
     double *mg_wtab = nullptr;       // inverse error by |ADC count| (thread-per-fit Migrad kernels)
     double mg_wtab_lsb = 0;          // the ADC step the table was built for
+    std::vector<int> local_cpus;     // cores of the NUMA node the GPU hangs off (within this process's affinity mask); empty = unknown
     cudaEvent_t last_use = nullptr;  // end of the last device-path call: later calls order themselves behind it (shared scratch, job lists, fit streams)
     bool last_use_valid = false;
     bool migrad_thread = true;       // env NPSWF_MIGRAD_THREAD=0: every Migrad fit through the warp-per-fit kernel
@@ -101,6 +102,11 @@ struct DevSlot {
     double pack_rate = 0;                                    // running estimate, bytes of doubles per second
     bool pack_unavailable = false;                           // the pinned staging buffers could not be allocated
     unsigned pack_probe = 0;                                 // chunks sent raw because the packer is slow
+    // measured rate of the raw (binary64) uploads from pinned memory: CUDA events around the raw part of a chunk
+    double dma_rate = 48.0e9;
+    cudaEvent_t dma_ev[2] = {nullptr, nullptr};
+    bool dma_pending = false;
+    double dma_bytes = 0;
 };
 
 }  // namespace
@@ -130,6 +136,57 @@ struct npswf_handle {
 };
 
 namespace {
+
+// Cores of the NUMA node a device is attached to, from sysfs (PCI bus id -> numa_node -> cpulist), intersected with
+// the affinity mask the process was started with.  The packer threads and the pinned staging buffers of a device are
+// placed there: with several GPUs on a two-socket host a staging buffer on the far socket halves the upload rate.
+// Empty when the topology is not visible (single node, container without sysfs) or NPSWF_NUMA_BIND=0.
+std::vector<int> device_local_cpus(int device)
+{
+    std::vector<int> out;
+    if (getenv("NPSWF_NUMA_BIND") && atoi(getenv("NPSWF_NUMA_BIND")) == 0) return out;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof bus, device) != cudaSuccess) { (void)cudaGetLastError(); return out; }
+    for (char *c = bus; *c; c++) *c = (char)tolower(*c);
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    int node = -1;
+    if (f) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+    if (node < 0) return out;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return out;
+    char buf[1024] = {0};
+    if (!fgets(buf, sizeof buf, f)) buf[0] = 0;
+    fclose(f);
+    cpu_set_t allowed;
+    CPU_ZERO(&allowed);
+    if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return out;
+    for (char *tok = strtok(buf, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        const int n = sscanf(tok, "%d-%d", &a, &b);
+        if (n == 1) b = a;
+        if (n >= 1)
+            for (int c = a; c <= b && c < CPU_SETSIZE; c++)
+                if (CPU_ISSET(c, &allowed)) out.push_back(c);
+    }
+    return out;
+}
+
+// scope guard: the calling thread runs next to the device while it packs and allocates staging memory
+struct ThreadBind {
+    cpu_set_t saved;
+    bool active = false;
+    explicit ThreadBind(const std::vector<int> &cpus)
+    {
+        if (cpus.empty()) return;
+        if (pthread_getaffinity_np(pthread_self(), sizeof saved, &saved) != 0) return;
+        active = true;
+        bind_this_thread(cpus);
+    }
+    ~ThreadBind() { if (active) (void)pthread_setaffinity_np(pthread_self(), sizeof saved, &saved); }
+};
 
 // temporary device buffer of the synchronous tap / stage entry points: freed on every return path
 template <class Tp>
@@ -639,6 +696,7 @@ int analyze_range_impl(npswf_handle *h, int d, int64_t lo, int64_t hi, const Hos
     int rc = wait_last_use(h, s);
     if (rc) return rc;
     if ((rc = ensure_io(h, s))) return rc;
+    ThreadBind bind(s.local_cpus);   // this thread packs a share of every chunk and first-touches the staging buffers
     // Host buffers: a three-stage pipeline over the two workspaces -- uploads on their own stream, every kernel on
     // the chunk's own stream, downloads on a
     // third stream -- so the copy engines of both directions run under the kernels of the neighbouring chunks.
@@ -658,7 +716,7 @@ int analyze_range_impl(npswf_handle *h, int d, int64_t lo, int64_t hi, const Hos
     bool pack = io.signal && !io.counts && !io.packed && h->pack_mode != 0 && !s.pack_unavailable;
     bool pinned_src = false;
     if (pack) {
-        if (!s.packer) s.packer.reset(new PackPool(h->pack_threads));
+        if (!s.packer) s.packer.reset(new PackPool(h->pack_threads, s.local_cpus));
         const size_t need = (size_t)std::min<int64_t>(chunk, hi - lo) * B * T;
         if (need > s.stage_cap) {
             s.stage_cap = 0;
@@ -770,13 +828,23 @@ int analyze_range_impl(npswf_handle *h, int d, int64_t lo, int64_t hi, const Hos
         if (pack) {
             double f = 0.0;
             if (h->pack_mode == 1 && pinned_src) {
-                const double a = 48.0e9 / s.pack_rate;
+                if (s.dma_pending && cudaEventQuery(s.dma_ev[1]) == cudaSuccess) {   // fold the last timed raw upload in
+                    float ms = 0;
+                    if (cudaEventElapsedTime(&ms, s.dma_ev[0], s.dma_ev[1]) == cudaSuccess && ms > 0)
+                        s.dma_rate = 0.5 * s.dma_rate + 0.5 * s.dma_bytes / (ms * 1e-3);
+                    s.dma_pending = false;
+                }
+                (void)cudaGetLastError();
+                const double a = s.dma_rate / s.pack_rate;
                 f = std::min(1.0, std::max(0.0, (a - 0.25) / (a + 0.75)));
                 if (f > 0.9) f = 1.0;
-                // a packer that slow is short of cores or of memory bandwidth (several ranks on one host): its reads
-                // would also slow the copy engine down (4 ranks: 1.51e8 packed 24 % at 18 GB/s, 1.70e8 raw), so the
-                // chunk goes over raw; a tenth of every 32nd chunk is packed to see whether that has changed
-                if (s.pack_rate < 30.0e9) f = ((++s.pack_probe & 31) == 0) ? 0.9 : 1.0;
+                // a packer far slower than the copy engine is short of cores or of memory bandwidth (several ranks on
+                // one host): its reads would also slow the copy engine down (4 ranks: 1.51e8 packed 24 % at 18 GB/s,
+                // 1.70e8 raw), so the chunk goes over raw
+                if (s.pack_rate < 0.6 * s.dma_rate) f = 1.0;
+                // keep both estimates alive: a tenth of every 32nd chunk goes the other way
+                if (f == 1.0 && (++s.pack_probe & 31) == 0) f = 0.9;
+                else if (f == 0.0 && (++s.pack_probe & 31) == 0) f = 0.1;
             } else if (h->pack_mode == 1 && s.pack_rate < 10.0e9) {
                 f = 1.0;   // pageable source and one or two slow host threads: the driver's staged upload is no slower
             }
@@ -788,8 +856,19 @@ int analyze_range_impl(npswf_handle *h, int d, int64_t lo, int64_t hi, const Hos
         if (k >= 3) CU_TRY(h, cudaStreamWaitEvent(s_in, w.ev_out, 0));
         if (pack) {
             // the raw part first: the copy engine works on it while the host packs the rest
-            if (n_raw > 0)
+            if (n_raw > 0) {
+                const bool timed = !s.dma_pending && pinned_src && n_raw >= 16;
+                if (timed) {
+                    if (!s.dma_ev[0]) { CU_TRY(h, cudaEventCreate(&s.dma_ev[0])); CU_TRY(h, cudaEventCreate(&s.dma_ev[1])); }
+                    CU_TRY(h, cudaEventRecord(s.dma_ev[0], s_in));
+                }
                 CU_TRY(h, cudaMemcpyAsync(w.signal, io.signal + ob * T, (size_t)n_raw * B * T * sizeof(double), cudaMemcpyHostToDevice, s_in));
+                if (timed) {
+                    CU_TRY(h, cudaEventRecord(s.dma_ev[1], s_in));
+                    s.dma_pending = true;
+                    s.dma_bytes = (double)n_raw * B * T * sizeof(double);
+                }
+            }
             if (n_cnt > 0) {
                 const int sb = (int)(k % 3);
                 const size_t off = (size_t)n_raw * B * T, cnt = (size_t)n_cnt * B * T;
@@ -1077,6 +1156,7 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
             return fail(NPSWF_ERR_CUDA);
         }
         s.sm_count = prop.multiProcessorCount;
+        s.local_cpus = device_local_cpus(s.device);
         int rc;
         if ((rc = dev_upload(h, s, &s.cal.mfyref, h->mfyref.data(), h->mfyref.size()))) return fail(rc);
         if ((rc = dev_upload(h, s, &s.cal.mfint, h->mfint.data(), h->mfint.size()))) return fail(rc);
@@ -1227,6 +1307,8 @@ void npswf_destroy(npswf_handle *h)
             if (s.stage[i]) cudaFreeHost(s.stage[i]);
             if (s.stage_ev[i]) cudaEventDestroy(s.stage_ev[i]);
         }
+        for (int i = 0; i < 2; i++)
+            if (s.dma_ev[i]) cudaEventDestroy(s.dma_ev[i]);
     }
     delete h;
 }
@@ -1261,6 +1343,17 @@ int npswf_host_packing_stats(const npswf_handle *h, int64_t *packed_chunks, int6
     if (raw_chunks) *raw_chunks = r;
     if (pack_gb_per_s) *pack_gb_per_s = sec > 0 ? bytes / sec / 1e9 : 0.0;
     if (packed_input_bytes) *packed_input_bytes = (int64_t)bytes;
+    return 0;
+}
+
+int npswf_host_upload_rate(const npswf_handle *h, double *raw_gb_per_s, int32_t *numa_bound_cpus)
+{
+    if (!h) return NPSWF_ERR_ARG;
+    double r = 0;
+    int cpus = 0;
+    for (const DevSlot &s : h->slots) { r += s.dma_rate; cpus += (int)s.local_cpus.size(); }
+    if (raw_gb_per_s) *raw_gb_per_s = h->slots.empty() ? 0.0 : r / (double)h->slots.size() / 1e9;
+    if (numa_bound_cpus) *numa_bound_cpus = cpus;
     return 0;
 }
 
