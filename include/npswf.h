@@ -164,6 +164,22 @@ int npswf_debug_pack_counts(const double *x, int64_t n, double lsb_mV, int32_t n
 int npswf_host_packing_stats(const npswf_handle *h, int64_t *packed_chunks, int64_t *raw_chunks, double *pack_gb_per_s,
                              int64_t *packed_input_bytes);
 
+/* ---- host-side callers of the hot path (plain C++, no device): SURVEY.md 8f-3 / 8f-4 ----
+ * npswf_hcana_pulses: T2:893-939 for one event -- corr_time_HMS from the first hcana pulse (T2:903; 0 if there is
+ * none, T2:557) and, per block, amplitude and time of the hcana pulse closest to the expected time timemean2[b]
+ * (T2:917-938; -100 where a block has none, T2:569-571).  adcCounter is not modified (the reference renumbers the
+ * scintillator channels 2000/2001 in place).  tdcoffset, timemean2: [NBLOCKS] Float_t as loaded at T2:368-375 / 526-529.
+ * Sampampl / Samptime [NBLOCKS] may be NULL. */
+int npswf_hcana_pulses(int32_t n_adc, const double *adcCounter, const double *adcSampPulseTime, const double *adcSampPulseTimeRaw,
+                       const double *adcSampPulseAmp, const float *tdcoffset, const float *timemean2, double *corr_time_HMS,
+                       double *Sampampl, double *Samptime);
+/* npswf_event_times: the h1time / h2time vectors of one event (T2:988-996) from its analysis outputs (padded
+ * [NBLOCKS][12] wftime / wfampl, wfnpulse, status): one entry per pulse with wfampl > 20 of every block that passed the
+ * cluster threshold, block order.  Returns the number of entries (<= sum of wfnpulse); h1time / h2time hold at least
+ * that many doubles (either may be NULL).  cortime: the calibration's [NBLOCKS] Float_t; dt: ns per sample. */
+int64_t npswf_event_times(const int32_t *wfnpulse, const double *wftime_padded, const double *wfampl_padded, const uint8_t *status,
+                          const float *cortime, double dt, double *h1time, double *h2time);
+
 /* Measured rate of the raw binary64 uploads out of the caller's pinned buffers (CUDA events around the raw part of a
  * chunk, running mean over the devices; 48 until something was measured), and the number of host cores the packer
  * threads / staging buffers are confined to (the cores of each GPU's NUMA node, from sysfs; 0 = topology not visible

@@ -10,6 +10,7 @@
 #ifndef NPSWF_HOST_HPP
 #define NPSWF_HOST_HPP
 #include <cstdint>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -22,12 +23,30 @@ struct EventResult {                      // what analyze() returns per event (T
     std::vector<int32_t> wfnpulse;              // [1080]
     std::vector<double> wfampl, wftime;         // flattened: blocks with pulses only, block order
     std::vector<int32_t> blockOffset;           // [1081]
-    std::vector<double> h2time;                 // wftime of the pulses with wfampl > 20, block order (T2:990-992)
+    std::vector<double> h1time, h2time;         // per pulse with wfampl > 20 of the fitted blocks, block order (T2:988-996)
 };
+
+// hcana pulse variables of one event (T2:893-939): what analyze() computes between the unpack and the block loop
+struct HcanaPulses {
+    double corr_time_HMS = 0.;                  // T2:903
+    std::vector<double> Sampampl, Samptime;     // [1080], -100 where the block has no hcana pulse
+};
+inline HcanaPulses hcana_pulses(int32_t NadcCounter, const double *adcCounter, const double *adcSampPulseTime,
+                                const double *adcSampPulseTimeRaw, const double *adcSampPulseAmp, const float *tdcoffset,
+                                const float *timemean2)
+{
+    HcanaPulses r;
+    r.Sampampl.resize(NPSWF_NBLOCKS);
+    r.Samptime.resize(NPSWF_NBLOCKS);
+    if (npswf_hcana_pulses(NadcCounter, adcCounter, adcSampPulseTime, adcSampPulseTimeRaw, adcSampPulseAmp, tdcoffset, timemean2,
+                           &r.corr_time_HMS, r.Sampampl.data(), r.Samptime.data()))
+        throw std::runtime_error("npswf_hcana_pulses: bad arguments");
+    return r;
+}
 
 class Analyzer {
 public:
-    Analyzer(const NpsWfConfig &cfg, const NpsWfCalib &calib)
+    Analyzer(const NpsWfConfig &cfg, const NpsWfCalib &calib) : cortime_(calib.cortime, calib.cortime + NPSWF_NBLOCKS), dt_(cfg.dt)
     {
         if (int rc = npswf_create(&cfg, &calib, &h_)) throw std::runtime_error(std::string("npswf_create: ") + npswf_last_error(nullptr) + " (" + std::to_string(rc) + ")");
     }
@@ -47,23 +66,18 @@ public:
     std::vector<EventResult> analyze(int64_t n_events, const double *signal, const int32_t *pres,
                                      const double *corr_time_HMS)
     {
-        // wfampl / wftime arrive already packed the reference's way (npswf_analyze_batch_flat): pools sized for 4 pulses
-        // per block on average first, for the 12-per-block maximum if that was not enough
+        // wfampl / wftime arrive already packed the reference's way (npswf_analyze_batch_flat).  The pools hold the
+        // 12-pulses-per-block maximum but are left uninitialised, so only the pages the pulses land in are ever touched:
+        // one call, no retry with a larger pool (which would run the whole batch -- and count its fits -- twice).
         const size_t nb = (size_t)n_events * NPSWF_NBLOCKS;
         std::vector<int32_t> n(nb), cnt((size_t)n_events);
         std::vector<int64_t> off((size_t)n_events);
-        std::vector<double> c(nb), tw(nb), aw(nb), pt, pa;
+        std::vector<double> c(nb), tw(nb), aw(nb);
         std::vector<uint8_t> st(nb);
-        for (int64_t per_block : {4, (int)NPSWF_MAXWFPULSES}) {
-            pt.resize(nb * (size_t)per_block);
-            pa.resize(pt.size());
-            const int rc = npswf_analyze_batch_flat(h_, n_events, signal, pres, corr_time_HMS, n.data(), off.data(), cnt.data(),
-                                                    pt.data(), pa.data(), (int64_t)pt.size(), c.data(), tw.data(), aw.data(),
-                                                    st.data(), nullptr);
-            if (rc == NPSWF_ERR_NOMEM && per_block < (int)NPSWF_MAXWFPULSES) continue;
-            check(rc);
-            break;
-        }
+        const size_t cap = nb * (size_t)NPSWF_MAXWFPULSES;
+        std::unique_ptr<double[]> pt(new double[cap ? cap : 1]), pa(new double[cap ? cap : 1]);
+        check(npswf_analyze_batch_flat(h_, n_events, signal, pres, corr_time_HMS, n.data(), off.data(), cnt.data(), pt.get(),
+                                       pa.get(), (int64_t)cap, c.data(), tw.data(), aw.data(), st.data(), nullptr));
         std::vector<EventResult> out((size_t)n_events);
         for (int64_t e = 0; e < n_events; e++) {
             EventResult &r = out[(size_t)e];
@@ -79,16 +93,21 @@ public:
                 run += r.wfnpulse[b];
             }
             r.blockOffset[NPSWF_NBLOCKS] = run;          // T2:1022
-            r.wftime.assign(pt.begin() + off[e], pt.begin() + off[e] + cnt[e]);
-            r.wfampl.assign(pa.begin() + off[e], pa.begin() + off[e] + cnt[e]);
-            // T2:987-996 runs for the blocks that were fitted (the others `continue` at T2:984): status bit okToFit
-            // is not returned here, chi2/wfnpulse tell the same -- a block with pulses that was not fitted keeps
-            // its times in bins and chi2 = -100 with no fall-back conversion; the reference skips it too
-            // (h1time needs Minuit's parameter objects and is not reproduced)
-            for (int b = 0; b < NPSWF_NBLOCKS; b++)
-                for (int p = 0; p < r.wfnpulse[b]; p++)
-                    if (st[o + b] & NPSWF_ST_OKTOFIT)
-                        if (r.wfampl[(size_t)r.blockOffset[b] + p] > 20) r.h2time.push_back(r.wftime[(size_t)r.blockOffset[b] + p]);
+            r.wftime.assign(pt.get() + off[e], pt.get() + off[e] + cnt[e]);
+            r.wfampl.assign(pa.get() + off[e], pa.get() + off[e] + cnt[e]);
+            // T2:988-996 runs for the blocks that passed the cluster threshold (the others `continue` at T2:984):
+            // h2time = wftime, h1time = fit parameter - timerefacc + corr_time_HMS/dt = (wftime + cortime) / dt
+            // (npswf_event_times), one entry per pulse with wfampl > 20
+            for (int b = 0; b < NPSWF_NBLOCKS; b++) {
+                if (!(st[o + b] & NPSWF_ST_OKTOFIT)) continue;
+                for (int p = 0; p < r.wfnpulse[b]; p++) {
+                    const size_t k = (size_t)r.blockOffset[b] + p;
+                    if (r.wfampl[k] > 20) {
+                        r.h2time.push_back(r.wftime[k]);
+                        r.h1time.push_back((r.wftime[k] + (double)cortime_[b]) / dt_);
+                    }
+                }
+            }
         }
         return out;
     }
@@ -148,7 +167,7 @@ private:
         }
     };
     // padded [E][1080][12] arrays -> the reference's flattened per-event vectors (T2:1289-1296)
-    static std::vector<EventResult> flatten(int64_t n_events, const Padded &p)
+    std::vector<EventResult> flatten(int64_t n_events, const Padded &p) const
     {
         std::vector<EventResult> out((size_t)n_events);
         for (int64_t e = 0; e < n_events; e++) {
@@ -165,6 +184,11 @@ private:
                                                     r.wftime.data(), r.wfampl.data(), r.blockOffset.data());
             r.wftime.resize((size_t)tot);
             r.wfampl.resize((size_t)tot);
+            std::vector<double> h1((size_t)tot + 1), h2((size_t)tot + 1);
+            const int64_t nt = npswf_event_times(&p.n[o], &p.t[o * NPSWF_MAXWFPULSES], &p.a[o * NPSWF_MAXWFPULSES], &p.st[o],
+                                                 cortime_.data(), dt_, h1.data(), h2.data());     // T2:988-996
+            r.h1time.assign(h1.begin(), h1.begin() + (nt > 0 ? nt : 0));
+            r.h2time.assign(h2.begin(), h2.begin() + (nt > 0 ? nt : 0));
         }
         return out;
     }
@@ -173,6 +197,8 @@ private:
         if (rc) throw std::runtime_error(std::string("npswf: ") + npswf_last_error(h_) + " (" + std::to_string(rc) + ")");
     }
     npswf_handle *h_ = nullptr;
+    std::vector<float> cortime_;
+    double dt_ = 4.0;
 };
 
 }  // namespace npswf

@@ -58,7 +58,7 @@ EXPORTS = [
     "npswf_device_timeref", "npswf_flatten_event", "npswf_debug_exp", "npswf_debug_exact_ops", "npswf_debug_fp64_peak", "npswf_unpack_batch", "npswf_analyze_batch_packed",
     "npswf_event_diagnostics_batch", "npswf_event_diagnostics_device", "npswf_set_profiling",
     "npswf_get_stage_times", "npswf_set_host_packing", "npswf_host_packing_stats", "npswf_debug_pack_counts", "npswf_analyze_batch_flat",
-    "npswf_analyze_batch_flat_i16", "npswf_host_upload_rate",
+    "npswf_analyze_batch_flat_i16", "npswf_host_upload_rate", "npswf_hcana_pulses", "npswf_event_times",
 ]
 
 _lib = None
@@ -425,6 +425,33 @@ class NpsWf:
         mm = np.zeros(2, np.uint64)
         self._check(lib().npswf_debug_exact_ops(self.h, C.c_int64(int(n_trials)), C.c_uint64(int(seed)), _p(mm)))
         return int(mm[0]), int(mm[1])
+
+
+def hcana_pulses(adcCounter, adcSampPulseTime, adcSampPulseTimeRaw, adcSampPulseAmp, tdcoffset, timemean2):
+    """T2:893-939 for one event: (corr_time_HMS, Sampampl[1080], Samptime[1080])."""
+    ac = _c(adcCounter, np.float64).ravel(); pt = _c(adcSampPulseTime, np.float64).ravel()
+    pr = _c(adcSampPulseTimeRaw, np.float64).ravel(); pa = _c(adcSampPulseAmp, np.float64).ravel()
+    td = _c(tdcoffset, np.float32).ravel(); tm = _c(timemean2, np.float32).ravel()
+    corr = C.c_double(0.0)
+    sa = np.zeros(NBLOCKS); stime = np.zeros(NBLOCKS)
+    rc = lib().npswf_hcana_pulses(C.c_int32(ac.size), _p(ac), _p(pt), _p(pr), _p(pa), _p(td), _p(tm), C.byref(corr), _p(sa), _p(stime))
+    if rc:
+        raise NpsWfError(rc, "npswf_hcana_pulses: bad arguments")
+    return corr.value, sa, stime
+
+
+def event_times(wfnpulse, wftime_padded, wfampl_padded, status, cortime, dt=4.0):
+    """T2:988-996 for one event: (h1time, h2time) from its analysis outputs."""
+    n = _c(wfnpulse, np.int32).reshape(NBLOCKS)
+    t = _c(wftime_padded, np.float64).reshape(NBLOCKS, MAXWFPULSES); a = _c(wfampl_padded, np.float64).reshape(NBLOCKS, MAXWFPULSES)
+    st = _c(status, np.uint8).reshape(NBLOCKS); ct = _c(cortime, np.float32).reshape(NBLOCKS)
+    h1 = np.zeros(NBLOCKS * MAXWFPULSES); h2 = np.zeros(NBLOCKS * MAXWFPULSES)
+    L = lib()
+    L.npswf_event_times.restype = C.c_int64
+    k = L.npswf_event_times(_p(n), _p(t), _p(a), _p(st), _p(ct), C.c_double(dt), _p(h1), _p(h2))
+    if k < 0:
+        raise NpsWfError(int(k), "npswf_event_times: bad arguments")
+    return h1[:k].copy(), h2[:k].copy()
 
 
 def shard_range(n_events, rank, world_size):

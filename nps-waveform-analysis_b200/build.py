@@ -32,13 +32,14 @@ def build(force=False, verbose=False):
         obj = os.path.join(HERE, "lib", "obj")
         os.makedirs(obj, exist_ok=True)
         vflag = ["-Xptxas", "-v"] if verbose else []
-        units = [("npswf_api.cu", []), ("npswf_migrad.cu", ["-fmad=false"]), ("host_pack.cpp", [])]
+        units = [("npswf_api.cu", []), ("npswf_migrad.cu", ["-fmad=false"]), ("host_pack.cpp", []), ("host_event.cpp", [])]
         hdr = os.path.join(ROOT, "include", "npswf.h")
-        migrad_only = {"npswf_migrad.cu", "kernel_fit_migrad.cuh", "migrad_core.hpp"}
+        migrad_only = {"npswf_migrad.cu", "kernel_fit_migrad.cuh", "migrad_core.hpp", "host_event.cpp"}
         deps = {
             "npswf_migrad.cu": [os.path.join(csrc, f) for f in ("npswf_migrad.cu", "kernel_fit_migrad.cuh", "migrad_core.hpp",
                                                                 "migrad_launch.hpp", "common.cuh")] + [hdr],
             "host_pack.cpp": [os.path.join(csrc, f) for f in ("host_pack.cpp", "host_pack.hpp")],
+            "host_event.cpp": [os.path.join(csrc, "host_event.cpp"), hdr],
             "npswf_api.cu": [os.path.join(csrc, f) for f in sorted(os.listdir(csrc)) if f not in migrad_only] + [hdr],
         }
         procs = []

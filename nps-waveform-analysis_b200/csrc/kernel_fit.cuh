@@ -41,8 +41,10 @@ __device__ __forceinline__ int tri(int a, int b) { return a * (a + 1) / 2 + b; }
 template <int PMAX, bool WITH_J>
 __device__ __forceinline__ double eval_points(const double *__restrict__ par, int N, int P, int lane,
                                               const double *y, const double *w, const double *__restrict__ spl,
-                                              FitSmem<PMAX> *sm)
+                                              FitSmem<PMAX> *sm, const double *__restrict__ knots = nullptr)
 {
+    // knots != nullptr: the spline's abscissae are not the sample indices (general interpX, T2:432): the interval
+    // comes from a bisection over the block's 110 knots (gsl_interp_bsearch), the offset from the knot itself
     double ss = 0;
 #pragma unroll
     for (int kk = 0; kk < 3; kk++) {
@@ -56,8 +58,18 @@ __device__ __forceinline__ double eval_points(const double *__restrict__ par, in
             const double d = x - tn;
             double s = 0, ds = 0;
             if (d > 1.0 && d < (double)(T - 1)) {  // T2:629
-                const int i = (int)d;
-                const double f = d - (double)i;
+                int i = (int)d;
+                double f = d - (double)i;
+                if (knots) {
+                    int lo = 0, hi = T - 1;
+                    while (hi > lo + 1) {
+                        const int m = (hi + lo) >> 1;
+                        if (knots[m] > d) hi = m;
+                        else lo = m;
+                    }
+                    i = lo;
+                    f = d - knots[lo];
+                }
                 const double4 q = *reinterpret_cast<const double4 *>(spl + 4 * i);
                 s = q.x + f * (q.y + f * (q.z + f * q.w));
                 if (WITH_J) ds = q.y + f * (2.0 * q.z + 3.0 * f * q.w);
@@ -134,16 +146,17 @@ struct LmOutcome { bool ok; double chi2; int iters; };
 // descent step exists any more.
 template <int PMAX>
 __device__ __forceinline__ LmOutcome lm_warp(FitSmem<PMAX> *sm, int N, int P, int lane, const double *y, const double *w,
-                                             const double *__restrict__ spl, int max_iter, double lambda0, double rel_tol)
+                                             const double *__restrict__ spl, int max_iter, double lambda0, double rel_tol,
+                                             const double *__restrict__ knots = nullptr)
 {
     double lambda = lambda0;
-    double chi2 = eval_points<PMAX, false>(sm->par, N, P, lane, y, w, spl, sm);
+    double chi2 = eval_points<PMAX, false>(sm->par, N, P, lane, y, w, spl, sm, knots);
     bool converged = false, newton = false;   // exact-Hessian steps once an accepted step gains < 5 %
     int it = 0;
     const int ntri = P * (P + 1) / 2;
     for (; it < max_iter; it++) {
         __syncwarp();
-        eval_points<PMAX, true>(sm->par, N, P, lane, y, w, spl, sm);
+        eval_points<PMAX, true>(sm->par, N, P, lane, y, w, spl, sm, knots);
         __syncwarp();
         // normal equations: entries spread over lanes
         for (int idx = lane; idx < ntri + P + N; idx += 32) {
@@ -155,8 +168,18 @@ __device__ __forceinline__ LmOutcome lm_warp(FitSmem<PMAX> *sm, int N, int P, in
                 for (int k = 0; k < NFIT; k++) {
                     const double d = (double)(MFSTART + k) - tn;
                     if (d > 1.0 && d < (double)(T - 1)) {
-                        const int i = (int)d;
-                        const double f = d - (double)i;
+                        int i = (int)d;
+                        double f = d - (double)i;
+                        if (knots) {
+                            int lo = 0, hi = T - 1;
+                            while (hi > lo + 1) {
+                                const int m = (hi + lo) >> 1;
+                                if (knots[m] > d) hi = m;
+                                else lo = m;
+                            }
+                            i = lo;
+                            f = d - knots[lo];
+                        }
                         const double2 q23 = *reinterpret_cast<const double2 *>(spl + 4 * i + 2);
                         s += sm->r[k] * sm->J[k * P] * (2.0 * q23.x + 6.0 * f * q23.y);
                     }
@@ -187,7 +210,7 @@ __device__ __forceinline__ LmOutcome lm_warp(FitSmem<PMAX> *sm, int N, int P, in
             }
             if (lane < P) sm->trial[lane] = sm->par[lane] + sm->dp[lane];
             __syncwarp();
-            const double c2 = eval_points<PMAX, false>(sm->trial, N, P, lane, y, w, spl, sm);
+            const double c2 = eval_points<PMAX, false>(sm->trial, N, P, lane, y, w, spl, sm, knots);
             if (c2 <= chi2) {
                 const double rel = (chi2 - c2) / (fabs(chi2) + 1e-30);
                 if (lane < P) sm->par[lane] = sm->trial[lane];
@@ -242,6 +265,7 @@ fit_kernel(const int *__restrict__ job_list, const int *__restrict__ job_count, 
         const int bn = (int)(item % B);
         const double *sig = signal + (size_t)item * T;
         const double *spl = cal.spline + (size_t)bn * (T - 1) * 4;
+        const double *knots = cal.knots_x ? cal.knots_x + (size_t)bn * T : nullptr;
         // BinData (T2:680-688) with Err of T2:946-956; stored as inverse error like ROOT::Fit::BinData
         double y[3], w[3];
 #pragma unroll
@@ -274,7 +298,7 @@ fit_kernel(const int *__restrict__ job_list, const int *__restrict__ job_count, 
         }
         __syncwarp();
         LmOutcome r = {false, 0.0, first_attempt_iters};
-        if (!first_done) r = lm_warp<PMAX>(sm, N, P, lane, y, w, spl, kp.fit_max_iter, 1e-3, FIT_REL_TOL);
+        if (!first_done) r = lm_warp<PMAX>(sm, N, P, lane, y, w, spl, kp.fit_max_iter, 1e-3, FIT_REL_TOL, knots);
         int st = 0;
         int iters = r.iters;
         if (r.ok) st = NPSWF_ST_FIT_OK1;
@@ -286,7 +310,7 @@ fit_kernel(const int *__restrict__ job_list, const int *__restrict__ job_count, 
                 sm->par[2 + 2 * lane] = seed_a;
             }
             __syncwarp();
-            r = lm_warp<PMAX>(sm, N, P, lane, y, w, spl, kp.fit_retry_max_iter, 1.0, FIT_REL_TOL);
+            r = lm_warp<PMAX>(sm, N, P, lane, y, w, spl, kp.fit_retry_max_iter, 1.0, FIT_REL_TOL, knots);
             iters += r.iters;
             if (r.ok) st = NPSWF_ST_FIT_OK2;
         }

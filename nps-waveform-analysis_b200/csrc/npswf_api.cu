@@ -127,6 +127,7 @@ struct npswf_handle {
     std::mutex mu;
     bool profiling = false;
     int fit_mode = NPSWF_FIT_FAST;
+    bool unit_knots = true;            // interpX of every block is 0..109: floor() indexing in the fast kernels
     int pack_mode = 1;                 // 0 off, 1 auto (on while it is faster than the raw upload), 2 always
     bool chunk_ramp = true;            // env NPSWF_CHUNK_RAMP=0: equal chunks in the host pipeline
     int pack_threads = 0;              // host threads per device
@@ -486,7 +487,7 @@ int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, cons
             // the reference's own minimiser (Migrad, numerical gradients, strategy 1 -> 2), one warp per fit
             MigradArgs ma{list, cnt, next, N, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr};
             const int cls = migrad_class(N);
-            if (N <= 3 && s.migrad_thread && s.occ_migrad_thread[N] > 0) {
+            if (N <= 3 && s.migrad_thread && s.occ_migrad_thread[N] > 0 && h->unit_knots) {
                 // one thread per fit for traces on the ADC lattice; anything else is handed to the warp-per-fit kernel
                 if (s.mg_wtab_lsb != h->pack_lsb) {   // (re)built on the stream that uses it first; later users are ordered behind it by the fork
                     CU_TRY(h, migrad_build_wtab(s.mg_wtab, h->pack_lsb, caller));
@@ -506,6 +507,14 @@ int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, cons
             } else {
                 CU_TRY(h, migrad_launch(cls, s.sm_count * s.occ_migrad[cls], st, ma));
             }
+        } else if (!h->unit_knots) {
+            // general interpX: the warp-per-fit LM kernel with a bisection per spline evaluation (both attempts)
+            if (N <= 6)
+                fit_kernel<13><<<s.sm_count * s.occ_fit_mid, FIT_THREADS, sizeof(FitSmem<13>) * FIT_WARPS, st>>>(
+                    list, cnt, N, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, 0, 0, next);
+            else
+                fit_kernel<25><<<s.sm_count * s.occ_fit_big, FIT_THREADS, sizeof(FitSmem<25>) * FIT_WARPS, st>>>(
+                    list, cnt, N, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, 0, 0, next);
         } else if (N <= 3 && s.fit_thread) {
             // thread-per-fit for the first tries of every fit, then the sub-warp kernel on the (rare) fits handed over
             int *ccnt = w.fit_count + 32 + N, *cnext = w.fit_count + 48 + N;
@@ -1082,14 +1091,19 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
                 return NPSWF_ERR_CALIB;
             }
         }
-        if (X[0] != 0.0 || X[T - 1] != (double)(T - 1)) {
-            // the kernels index the spline by floor(x): knots must be the sample indices 0..109
+        {   // the fast kernels index the spline by floor(x): that needs the knots to be the sample indices 0..109.  Any
+            // other strictly increasing interpX (T2:432) takes the generic-knot path (bisection per evaluation, as GSL
+            // does); it must cover the model's guard interval 1 < x - t < 109 (T2:629), outside of which the reference
+            // would evaluate GSL's spline out of its domain.
             bool unit = true;
             for (int it = 0; it < T; it++) unit = unit && (X[it] == (double)it);
             if (!unit) {
-                g_create_error = "npswf_create: interpX must be the sample indices 0..109 (unit knots)";
-                delete h;
-                return NPSWF_ERR_CALIB;
+                h->unit_knots = false;
+                if (X[0] > 1.0 || X[T - 1] < (double)(T - 1)) {
+                    g_create_error = "npswf_create: interpX must cover [1, 109] (the model evaluates the spline on 1 < x - t < 109)";
+                    delete h;
+                    return NPSWF_ERR_CALIB;
+                }
             }
         }
         if (h->mfint[i] == 0.0) {
@@ -1186,6 +1200,7 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
         if ((rc = dev_upload(h, s, &s.cal.cortime, cal->cortime, (size_t)B))) return fail(rc);
         if ((rc = dev_upload(h, s, &s.cal.preswf, cal->preswf, (size_t)B))) return fail(rc);
         if ((rc = dev_upload(h, s, &s.cal.spline, h->spline.data(), h->spline.size()))) return fail(rc);
+        if (!h->unit_knots && (rc = dev_upload(h, s, &s.cal.knots_x, cal->interpX, (size_t)B * T))) return fail(rc);
         {   // knot form (y_i, c_i), zero padded: S on [i, i+1] from the two knots (kernel_fit_thread.cuh)
             std::vector<double2> kn((size_t)B * KN_LEN, make_double2(0.0, 0.0));
             for (int b = 0; b < B; b++) {

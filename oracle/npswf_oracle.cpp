@@ -521,6 +521,73 @@ extern "C" void oracle_event_diagnostics(const double *signal, double *ampl, dou
     *integtot = it_;
 }
 
+// hcana pulse variables and the HMS time correction of analyze (/root/reference/TEST_2.C:893-939), one event.
+// adcCounter is renumbered in place as the reference does (T2:895-898).  Deviation (SURVEY.md App. B spirit): the
+// reference indexes tdcoffset[nblocks] with counters 1080 / 1081 (first pulse from a scintillator) -- out of bounds;
+// here such a first pulse takes offset 0.
+extern "C" void oracle_hcana_pulses(int32_t NadcCounter, double *adcCounter, const double *adcSampPulseTime,
+                                    const double *adcSampPulseTimeRaw, const double *adcSampPulseAmp, const float *tdcoffset,
+                                    const float *timemean2, double *corr_time_HMS, double *Sampampl, double *Samptime)
+{
+    std::vector<int> Npulse(B, 0);
+    for (int i = 0; i < B; i++) { Sampampl[i] = -100; Samptime[i] = -100; }   // T2:569-571
+    *corr_time_HMS = 0.;                                                       // T2:557
+    for (int iNdata = 0; iNdata < NadcCounter; iNdata++) {
+        if (adcCounter[iNdata] == 2000) adcCounter[iNdata] = 1080;
+        if (adcCounter[iNdata] == 2001) adcCounter[iNdata] = 1081;
+        if (iNdata == 0) {                                                     // T2:901-904
+            const int c = (int)(adcCounter[iNdata]);
+            const double off = (c >= 0 && c < B) ? (double)tdcoffset[c] : 0.0;
+            *corr_time_HMS = adcSampPulseTime[iNdata] - (adcSampPulseTimeRaw[iNdata] / 16.) - off;
+        }
+        if (adcCounter[iNdata] >= 0 && adcCounter[iNdata] < B) {               // T2:917-938
+            const int c = (int)(adcCounter[iNdata]);
+            Npulse[c] += 1;
+            if (Npulse[c] == 1) {
+                Sampampl[c] = adcSampPulseAmp[iNdata];
+                Samptime[c] = adcSampPulseTime[iNdata];
+            }
+            if (Npulse[c] > 1) {
+                if (std::abs(Samptime[c] - timemean2[c]) > std::abs(adcSampPulseTime[iNdata] - timemean2[c])) {
+                    Sampampl[c] = adcSampPulseAmp[iNdata];
+                    Samptime[c] = adcSampPulseTime[iNdata];
+                }
+            }
+        }
+    }
+}
+
+// h1time / h2time of one event as analyze fills them (T2:988-996): the block loop is run again, keeping what the
+// reference reads there -- finter[i]->GetParameter(1 + 2p), i.e. the fitted bin offset after a successful fit
+// (T2:818-822) and the seed (wftime - timeref, T2:662) after a failed one.  Returns the number of entries.
+extern "C" int oracle_event_times(const OracleHandle *h, const double *sig, const int32_t *pres, double corr, double *h1time,
+                                  double *h2time)
+{
+    int n = 0;
+    const double dt = h->cfg.dt, timerefacc = h->cfg.timerefacc;
+    for (int i = 0; i < B; i++) {
+        if (!(pres[i] == 1 && h->preswf[i] == 1)) continue;
+        double minsignal = 1e6;
+        for (int it = 0; it < T; it++) minsignal = std::min(minsignal, sig[i * T + it]);
+        double wt[MAXP], wa[MAXP], par[2 * MAXP + 1], seed_off[MAXP];
+        for (int p = 0; p < MAXP; p++) { wt[p] = -999; wa[p] = -999; }
+        const int np = oracle_find_pulses_mf(h, i, sig, pres, minsignal, wt, wa);
+        if (!oracle_pass_cluster_threshold(h, i, sig, pres)) continue;         // T2:980-986
+        for (int p = 0; p < np; p++) seed_off[p] = wt[p] - h->timeref[i];
+        double chi2;
+        const int st = fitwf_impl(h, i, sig, np, corr, wt, wa, &chi2, nullptr, par);
+        for (int p = 0; p < np; p++) {
+            if (wa[p] > 20) {
+                const double param = (st & OR_ST_FALLBACK) ? seed_off[p] : par[1 + 2 * p];
+                h2time[n] = wt[p];
+                h1time[n] = param - timerefacc + corr / dt;
+                n++;
+            }
+        }
+    }
+    return n;
+}
+
 extern "C" int oracle_analyze_batch(const OracleHandle *h, int64_t n_events, const double *signal, const int32_t *pres,
                                     const double *corr_time_HMS, int32_t *wfnpulse, double *wftime, double *wfampl,
                                     double *chi2, double *timewf, double *amplwf, uint8_t *status, int32_t *ncalls,

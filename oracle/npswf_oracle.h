@@ -98,6 +98,13 @@ int oracle_unpack_event(const double *samp, int64_t n_words, double *signal /*[B
                         double *minsignal /*[B] or NULL*/);
 void oracle_event_diagnostics(const double *signal /*[B*T]*/, double *ampl /*[B]*/, double *enertot, double *integtot);
 
+/* HMS correction + hcana pulse selection T2:893-939; h1time / h2time of an event T2:988-996 */
+void oracle_hcana_pulses(int32_t NadcCounter, double *adcCounter, const double *adcSampPulseTime, const double *adcSampPulseTimeRaw,
+                         const double *adcSampPulseAmp, const float *tdcoffset /*[B]*/, const float *timemean2 /*[B]*/,
+                         double *corr_time_HMS, double *Sampampl /*[B]*/, double *Samptime /*[B]*/);
+int oracle_event_times(const OracleHandle *h, const double *signal_event, const int32_t *pres, double corr_time_HMS,
+                       double *h1time /*[B*12]*/, double *h2time /*[B*12]*/);
+
 int oracle_search_highres(const double *source, int ssize, double sigma, double threshold, int decon_iterations,
                           int aver_window, int max_peaks, double *pos_x, double *smoothed_out, double *decon_out,
                           int use_libm_exp);

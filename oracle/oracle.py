@@ -115,6 +115,17 @@ def event_diagnostics(signal_event):
     return ampl, float(et.value), float(it.value)
 
 
+def hcana_pulses(adcCounter, adcSampPulseTime, adcSampPulseTimeRaw, adcSampPulseAmp, tdcoffset, timemean2):
+    """T2:893-939 for one event: (corr_time_HMS, Sampampl[1080], Samptime[1080])."""
+    L = lib()
+    ac = _c(adcCounter, np.float64).ravel().copy(); pt = _c(adcSampPulseTime, np.float64).ravel()
+    pr = _c(adcSampPulseTimeRaw, np.float64).ravel(); pa = _c(adcSampPulseAmp, np.float64).ravel()
+    td = _c(tdcoffset, np.float32).ravel(); tm = _c(timemean2, np.float32).ravel()
+    corr = C.c_double(0.0); sa = np.zeros(NBLOCKS); st = np.zeros(NBLOCKS)
+    L.oracle_hcana_pulses(C.c_int32(ac.size), _p(ac), _p(pt), _p(pr), _p(pa), _p(td), _p(tm), C.byref(corr), _p(sa), _p(st))
+    return corr.value, sa, st
+
+
 def migrad(fcn, start, step, strategy=1, maxfcn=0, tolerance=0.01):
     """Minuit2 Migrad restatement on a Python chi2 callable (unit tests)."""
     L = lib()
@@ -200,6 +211,15 @@ class Oracle:
         st = lib().oracle_fitwf(self.h, C.c_int(bn), _p(sig), C.c_int(npulse), C.c_double(corr_time_HMS),
                                 _p(t), _p(a), C.byref(chi2), C.byref(nc), _p(raw))
         return dict(status=st, wftime=t, wfampl=a, chi2=chi2.value, ncalls=nc.value, params=raw[:2 * npulse + 1])
+
+    def event_times(self, signal_event, pres, corr_time_HMS=0.0):
+        """(h1time, h2time) of one event as analyze fills them (T2:988-996)."""
+        sig = _c(signal_event, np.float64).reshape(NBLOCKS, NTIME)
+        pr = _c(pres, np.int32)
+        h1 = np.zeros(NBLOCKS * MAXP); h2 = np.zeros(NBLOCKS * MAXP)
+        lib().oracle_event_times.restype = C.c_int
+        n = lib().oracle_event_times(self.h, _p(sig), _p(pr), C.c_double(corr_time_HMS), _p(h1), _p(h2))
+        return h1[:n].copy(), h2[:n].copy()
 
     def analyze_batch(self, signal, pres, corr_time_HMS, n_threads=1):
         sig = _c(signal, np.float64).reshape(-1, NBLOCKS, NTIME)

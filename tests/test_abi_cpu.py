@@ -127,3 +127,16 @@ def test_host_packer_accepts_exactly_the_lattice(pkg, calib, spline):
     assert pkg.pack_counts(np.arange(-50, 50) * 0.5, 0.5)[0]
     assert not pkg.pack_counts(np.arange(-50, 50) * 0.25, 0.5)[0]
     assert pkg.pack_counts(np.zeros(0), lsb)[0]
+
+
+def test_root_macro_typechecks_against_host_mirror():
+    """macros/npsWF_gpu.C cannot run here (no ROOT), but it must at least compile against include/npswf_host.hpp:
+    type-checked with stub ROOT headers (tests/cpp/mock_root), and it must fill the 17 WF columns of T2:1387."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(root, "tests", "cpp", "mock_root"),
+                           "-I", os.path.join(root, "include"), "-x", "c++", os.path.join(root, "macros", "npsWF_gpu.C")])
+    src = open(os.path.join(root, "macros", "npsWF_gpu.C")).read()
+    for col in ("chi2", "ampl", "amplwf", "wfnpulse", "Sampampl", "Samptime", "timewf", "enertot", "integtot", "pres",
+                "corr_time_HMS", "h1time", "h2time", "runnum", "evt", "wfampl", "wftime"):
+        assert 'Branch("%s"' % col in src, col

@@ -151,3 +151,41 @@ def test_migrad_mode_device_path_and_counters(pkg, calib, spline):
     torch.cuda.synchronize()
     for k in host:
         assert np.array_equal(o[k].cpu().numpy(), host[k]), k
+
+
+def test_general_interpx_knots(pkg, calib, spline):
+    """interpX need not be the sample indices (T2:432 reads the knots from the reference-waveform file): any strictly
+    increasing knots covering [1, 109] take the generic-knot path (bisection per spline evaluation, as GSL's
+    gsl_interp_bsearch).  MIGRAD mode: every output bit-identical to the oracle; FAST mode: everything but the fit
+    results exact, fits within tolerance; knots that do not cover the guard interval are refused."""
+    threads = os.cpu_count() or 1
+    it = np.arange(110.0)
+    x = it + 0.3 * np.sin(0.37 * it)
+    x[0], x[109] = 0.0, 109.0
+    assert (np.diff(x) > 0).all()
+    cal = dict(calib)
+    cal["interpX"] = np.tile(x, (1080, 1))
+    # the same physical shapes sampled at the new knots (natural spline of the unit-knot calibration evaluated there)
+    orc0 = oracle.Oracle(calib)
+    y = np.empty((1080, 110))
+    for b in range(1080):
+        y[b] = np.where((x > 0) & (x < 109), orc0.spline_eval(b, np.clip(x, 0.0, 108.999999)), calib["interpY"][b][np.clip(np.rint(x).astype(int), 0, 109)])
+    cal["interpY"] = y
+    cal["timeref"] = cal["interpX"][np.arange(1080), y.argmax(axis=1)].copy()      # T2:434-438
+    orc = oracle.Oracle(cal)
+    ev = synth.generate_host(synth.config_params(2, absent_frac=0.02), spline, calib, 43_000_000, 16, n_threads=threads)
+    ref = orc.analyze_batch(ev["signal"], ev["pres"], ev["corr_time_HMS"], n_threads=threads)
+    hm = pkg.NpsWf(cal, fit_mode=pkg.FIT_MIGRAD)
+    assert np.array_equal(hm.spline_coeffs(), orc.spline_coeffs())
+    got = hm.analyze(ev["signal"], ev["pres"], ev["corr_time_HMS"])
+    for k in ("wfnpulse", "status", "wftime", "wfampl", "chi2", "timewf", "amplwf"):
+        assert np.array_equal(got[k], ref[k]), k
+    hf = pkg.NpsWf(cal)
+    fg = hf.analyze(ev["signal"], ev["pres"], ev["corr_time_HMS"])
+    assert np.array_equal(fg["wfnpulse"], ref["wfnpulse"]) and np.array_equal(fg["status"] & 3, ref["status"] & 3)
+    both, good = _agreement(ref, fg)
+    assert both.sum() > 10000 and good[both].mean() >= 0.99, (int(both.sum()), float(good[both].mean()))
+    bad = dict(cal)
+    bad["interpX"] = cal["interpX"] + 2.0            # starts at 2: does not cover the guard interval
+    with pytest.raises(pkg.NpsWfError):
+        pkg.NpsWf(bad)

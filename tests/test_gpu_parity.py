@@ -760,3 +760,21 @@ def test_non_finite_samples_end_as_fallback(pkg, gpu, orc, calib, events):
         assert (rm["status"][0, b] & 28) == o["status"], (b, rm["status"][0, b], o["status"])
         assert np.array_equal(rm["chi2"][0, b], o["chi2"], equal_nan=True)
         assert np.array_equal(rm["wftime"][0, b, :n[0, b]], o["wftime"][:n[0, b]], equal_nan=True)
+
+
+def test_event_times_h1time_h2time(pkg, gpu, orc, calib, events):
+    """h1time / h2time (T2:988-996) from the analysis outputs (npswf_event_times) against the oracle, which reads the
+    fit parameters as the reference does.  MIGRAD mode: h2time exact, h1time = (wftime + cortime) / dt within 1e-12
+    relative of parameter - timerefacc + corr/dt (one rounding of the round trip through the corrected time)."""
+    hm = pkg.NpsWf(calib, fit_mode=pkg.FIT_MIGRAD)
+    n_seen = 0
+    for cfg in (2, 3):
+        ev = events[cfg]
+        got = hm.analyze(ev["signal"], ev["pres"], ev["corr_time_HMS"])
+        for e in range(ev["signal"].shape[0]):
+            h1, h2 = pkg.event_times(got["wfnpulse"][e], got["wftime"][e], got["wfampl"][e], got["status"][e], calib["cortime"])
+            r1, r2 = orc.event_times(ev["signal"][e], ev["pres"][e], ev["corr_time_HMS"][e])
+            assert np.array_equal(h2, r2), (cfg, e)
+            assert h1.shape == r1.shape and np.allclose(h1, r1, rtol=1e-12, atol=1e-12), (cfg, e, np.abs(h1 - r1).max())
+            n_seen += h1.size
+    assert n_seen > 1000

@@ -6,5 +6,5 @@ cd "$(dirname "$0")/.."
 tag=$1; shift
 P=nps-waveform-analysis_b200
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -fmad=false "$@" -c -o $P/lib/obj/npswf_migrad_$tag.o $P/csrc/npswf_migrad.cu
-/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $P/lib/libnpswf_$tag.so $P/lib/obj/npswf_api.o $P/lib/obj/npswf_migrad_$tag.o $P/lib/obj/host_pack.o
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $P/lib/libnpswf_$tag.so $P/lib/obj/npswf_api.o $P/lib/obj/npswf_migrad_$tag.o $P/lib/obj/host_pack.o $P/lib/obj/host_event.o
 echo built $P/lib/libnpswf_$tag.so
