@@ -588,6 +588,37 @@ extern "C" int oracle_event_times(const OracleHandle *h, const double *sig, cons
     return n;
 }
 
+// FindPulsesMF for every block of n_events events, event-parallel (no fits): what the exp / FMA sensitivity study of
+// the peak search runs over 10^6 spectra (tools/exp_flip_rate.py).
+extern "C" int oracle_find_pulses_batch(const OracleHandle *h, int64_t n_events, const double *signal, const int32_t *pres,
+                                        int32_t *wfnpulse, double *wftime, double *wfampl, int n_threads)
+{
+    if (n_threads < 1) n_threads = 1;
+    std::atomic<int64_t> next{0};
+    auto worker = [&]() {
+        for (;;) {
+            const int64_t e = next.fetch_add(1);
+            if (e >= n_events) break;
+            const double *sig = signal + (size_t)e * B * T;
+            const int32_t *pr = pres + (size_t)e * B;
+            for (int i = 0; i < B; i++) {
+                double *wt = wftime + ((size_t)e * B + i) * MAXP, *wa = wfampl + ((size_t)e * B + i) * MAXP;
+                for (int p = 0; p < MAXP; p++) { wt[p] = -999; wa[p] = -999; }
+                wfnpulse[(size_t)e * B + i] = 0;
+                if (!(pr[i] == 1 && h->preswf[i] == 1)) continue;
+                double minsignal = 1e6;
+                for (int it = 0; it < T; it++) minsignal = std::min(minsignal, sig[i * T + it]);
+                wfnpulse[(size_t)e * B + i] = oracle_find_pulses_mf(h, i, sig, pr, minsignal, wt, wa);
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; t++) th.emplace_back(worker);
+    worker();
+    for (auto &t : th) t.join();
+    return 0;
+}
+
 extern "C" int oracle_analyze_batch(const OracleHandle *h, int64_t n_events, const double *signal, const int32_t *pres,
                                     const double *corr_time_HMS, int32_t *wfnpulse, double *wftime, double *wfampl,
                                     double *chi2, double *timewf, double *amplwf, uint8_t *status, int32_t *ncalls,

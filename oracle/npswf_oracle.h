@@ -92,6 +92,10 @@ int oracle_analyze_batch(const OracleHandle *h, int64_t n_events, const double *
                          double *chi2 /*[E][B]*/, double *timewf /*[E][B]*/, double *amplwf /*[E][B]*/,
                          uint8_t *status /*[E][B]*/, int32_t *ncalls /*[E][B] or NULL*/, int n_threads);
 
+/* FindPulsesMF for all blocks of a batch (no fits), event-parallel */
+int oracle_find_pulses_batch(const OracleHandle *h, int64_t n_events, const double *signal, const int32_t *pres,
+                             int32_t *wfnpulse, double *wftime /*[E][B][12]*/, double *wfampl, int n_threads);
+
 /* TSpectrum restatement (tspectrum.cpp) */
 /* callers on either side of the hot path: waveform unpack T2:830-889, diagnostics T2:1026-1056 */
 int oracle_unpack_event(const double *samp, int64_t n_words, double *signal /*[B*T]*/, int32_t *pres /*[B]*/,

@@ -143,8 +143,16 @@ class Oracle:
     """Handle over (config, calibration): mirrors the reference's file-scope globals (T2:51-85)."""
 
     def __init__(self, calib, specthres=0.02, mfthres=1.5, trig_thres=10.0, coinc_width=20, dt=4.0,
-                 timerefacc=0.0, flags=0):
-        L = lib()
+                 timerefacc=0.0, flags=0, lib_path=None):
+        # lib_path: another build of the same restatement (the FMA-contracted one of `make -C oracle fma`)
+        if lib_path is None:
+            L = lib()
+        else:
+            L = C.CDLL(lib_path)
+            L.oracle_create.restype = C.c_void_p
+            L.oracle_create.argtypes = [C.POINTER(_Cfg), C.POINTER(_Cal)]
+            L.oracle_destroy.argtypes = [C.c_void_p]
+        self._lib = L
         self._keep = dict(
             interpX=_c(calib["interpX"], np.float64), interpY=_c(calib["interpY"], np.float64),
             timeref=_c(calib["timeref"], np.float64), cortime=_c(calib["cortime"], np.float32),
@@ -158,7 +166,7 @@ class Oracle:
     def __del__(self):
         try:
             if self.h:
-                lib().oracle_destroy(self.h); self.h = None
+                self._lib.oracle_destroy(self.h); self.h = None
         except Exception:
             pass
 
@@ -220,6 +228,15 @@ class Oracle:
         lib().oracle_event_times.restype = C.c_int
         n = lib().oracle_event_times(self.h, _p(sig), _p(pr), C.c_double(corr_time_HMS), _p(h1), _p(h2))
         return h1[:n].copy(), h2[:n].copy()
+
+    def find_pulses_batch(self, signal, pres, n_threads=1):
+        """FindPulsesMF for every block of a batch (no fits): (wfnpulse[E,1080], wftime[E,1080,12], wfampl[E,1080,12])."""
+        sig = _c(signal, np.float64).reshape(-1, NBLOCKS, NTIME)
+        E = sig.shape[0]
+        pr = _c(pres, np.int32).reshape(E, NBLOCKS)
+        n = np.zeros((E, NBLOCKS), np.int32); t = np.zeros((E, NBLOCKS, MAXP)); a = np.zeros((E, NBLOCKS, MAXP))
+        self._lib.oracle_find_pulses_batch(self.h, C.c_int64(E), _p(sig), _p(pr), _p(n), _p(t), _p(a), C.c_int(n_threads))
+        return n, t, a
 
     def analyze_batch(self, signal, pres, corr_time_HMS, n_threads=1):
         sig = _c(signal, np.float64).reshape(-1, NBLOCKS, NTIME)
