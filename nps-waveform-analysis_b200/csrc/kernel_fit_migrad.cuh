@@ -86,6 +86,7 @@ struct MgWarpFcn {
         }
         return chi2;
     }
+    MG_DEFAULT_PAIR(__device__ __forceinline__)
 };
 
 template <int PMAX>
@@ -263,6 +264,65 @@ struct MgThreadFcn {
             chi2 += tmp * tmp;
         }
         return chi2;
+    }
+    // chi2 at x with x[i] = vp and with x[i] = vm in ONE pass over the samples (every central difference of Migrad and
+    // MnHesse): sample, weight and the spline terms of the untouched pulses are shared, each of the two sums is built
+    // with exactly the operations of operator() in the same order, so f1 and f2 carry the same bits as two calls.
+    __device__ MT_FCN_ATTR void pair(double *x, int i, double vp, double vm, double &f1, double &f2)
+    {
+        ncalls += 2;
+        double t[N], A[N];
+#pragma unroll
+        for (int n = 0; n < N; n++) { t[n] = x[1 + 2 * n]; A[n] = x[2 + 2 * n]; }
+        const bool ped = i == 0, is_t = (i & 1) != 0;
+        const int m = (i - 1) >> 1;                       // pulse of parameter i (i > 0): t_m = x[1+2m], A_m = x[2+2m]
+        const double p1 = ped ? vp : x[0], p2 = ped ? vm : x[0];
+        double c1 = 0, c2 = 0;
+#pragma unroll 2
+        for (int k = 0; k < mg::FIT_NPT; k++) {
+            const int c = col[k * MT_THREADS];
+            const double y = (double)c * lsb;
+            const double w = __ldg(wtab + abs(c));
+            const double xk = (double)(mg::FIT_X0 + k);
+            double v1 = p1, v2 = p2;
+#pragma unroll
+            for (int n = 0; n < N; n++) {
+                if (is_t && n == m) {                     // the pulse whose time is varied: two spline evaluations
+                    const double d1 = xk - vp, d2 = xk - vm;
+                    if (d1 > 1 && d1 < mg::FIT_T - 1) {
+                        const int j = (int)d1;
+                        const double delx = d1 - (double)j;
+                        const double2 c01 = __ldg(reinterpret_cast<const double2 *>(spl + 4 * j));
+                        const double2 c23 = __ldg(reinterpret_cast<const double2 *>(spl + 4 * j) + 1);
+                        v1 += A[n] * (c01.x + delx * (c01.y + delx * (c23.x + delx * c23.y)));
+                    }
+                    if (d2 > 1 && d2 < mg::FIT_T - 1) {
+                        const int j = (int)d2;
+                        const double delx = d2 - (double)j;
+                        const double2 c01 = __ldg(reinterpret_cast<const double2 *>(spl + 4 * j));
+                        const double2 c23 = __ldg(reinterpret_cast<const double2 *>(spl + 4 * j) + 1);
+                        v2 += A[n] * (c01.x + delx * (c01.y + delx * (c23.x + delx * c23.y)));
+                    }
+                } else {
+                    const double dt0 = xk - t[n];
+                    if (dt0 > 1 && dt0 < mg::FIT_T - 1) {
+                        const int j = (int)dt0;
+                        const double delx = dt0 - (double)j;
+                        const double2 c01 = __ldg(reinterpret_cast<const double2 *>(spl + 4 * j));
+                        const double2 c23 = __ldg(reinterpret_cast<const double2 *>(spl + 4 * j) + 1);
+                        const double sv = c01.x + delx * (c01.y + delx * (c23.x + delx * c23.y));
+                        const bool amp = !ped && !is_t && n == m;     // the pulse whose amplitude is varied
+                        v1 += (amp ? vp : A[n]) * sv;
+                        v2 += (amp ? vm : A[n]) * sv;
+                    }
+                }
+            }
+            const double r1 = (y - v1) * w, r2 = (y - v2) * w;
+            c1 += r1 * r1;
+            c2 += r2 * r2;
+        }
+        f1 = c1;
+        f2 = c2;
     }
 };
 

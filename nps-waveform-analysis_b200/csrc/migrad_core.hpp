@@ -8,7 +8,10 @@
 // so that ONE executor runs it -- lane 0 of a warp in fit_migrad_kernel (the other lanes only serve chi2
 // evaluations), or a host thread in tests/cpp/migrad_core_host.cpp -- on a fixed workspace with no allocation, no
 // recursion and no libm beyond sqrt/fabs.  The chi2 comes in as a functor: `double fcn(const double *x)`, counting
-// its own calls in `fcn.ncalls`.
+// its own calls in `fcn.ncalls`, plus `fcn.pair(x, i, vp, vm, f1, f2)`: f1 = chi2 at x with x[i] = vp, f2 = the same with
+// x[i] = vm (x[i] itself is left alone; two calls) -- every central difference of Migrad and MnHesse is such a pair,
+// and an implementation may share what the two evaluations have in common as long as each value keeps its bits
+// (MG_DEFAULT_PAIR is the plain two-call version).
 //
 // The translation unit that instantiates this for the device is compiled with -fmad=false: Minuit2 in ROOT is
 // built without FMA contraction (x86-64 baseline), and every comparison below (step tolerances, EDM goal, line-search
@@ -21,6 +24,16 @@
 #else
 #define MG_HD
 #endif
+
+// the plain implementation of Fcn::pair: two evaluations
+#define MG_DEFAULT_PAIR(QUAL)                                                                 \
+    QUAL void pair(double *x, int i, double vp, double vm, double &f1, double &f2)            \
+    {                                                                                         \
+        const double keep = x[i];                                                             \
+        x[i] = vp; f1 = (*this)(x);                                                           \
+        x[i] = vm; f2 = (*this)(x);                                                           \
+        x[i] = keep;                                                                          \
+    }
 
 namespace npswf {
 namespace mg {
@@ -247,11 +260,8 @@ MG_HD inline void numerical_gradient(Fcn &fcn, const double *x, double fcnmin, d
             if (fabs((step - stepb4) / step) < st.grad_step_tol) break;
             gsi = step;
             stepb4 = step;
-            xw[i] = xtf + step;
-            const double fs1 = fcn(xw);
-            xw[i] = xtf - step;
-            const double fs2 = fcn(xw);
-            xw[i] = xtf;
+            double fs1, fs2;
+            fcn.pair(xw, i, xtf + step, xtf - step, fs1, fs2);
             const double grdb4 = gi;
             gi = 0.5 * (fs1 - fs2) / step;
             g2i = (fs1 + fs2 - 2. * fcnmin) / step / step;
@@ -446,9 +456,7 @@ MG_HD inline void hesse(Fcn &fcn, Work<PMAX> &W, Scal &S, int n, const Strategy 
             double sag = 0., fs1 = 0., fs2 = 0.;
             bool got = false;
             for (int multpy = 0; multpy < 5; multpy++) {
-                x[i] = xtf + d; fs1 = fcn(x);
-                x[i] = xtf - d; fs2 = fcn(x);
-                x[i] = xtf;
+                fcn.pair(x, i, xtf + d, xtf - d, fs1, fs2);
                 sag = 0.5 * (fs1 + fs2 - 2. * amin);
                 if (sag != 0) { got = true; break; }
                 d *= 10.;
@@ -494,10 +502,8 @@ MG_HD inline void hesse(Fcn &fcn, Work<PMAX> &W, Scal &S, int n, const Strategy 
             double chgold = 10000.;
             for (int j = 0; j < st.hess_grad_ncyc; j++) {
                 for (int k = 0; k < n; k++) xp[k] = W.x[k];
-                xp[i] = xtf + d;
-                const double fs1 = fcn(xp);
-                xp[i] = xtf - d;
-                const double fs2 = fcn(xp);
+                double fs1, fs2;
+                fcn.pair(xp, i, xtf + d, xtf - d, fs1, fs2);
                 const double grdold = grd[i];
                 const double grdnew = (fs1 - fs2) / (2. * d);
                 const double dgmin = EPS * (fabs(fs1) + fabs(fs2)) / d;

@@ -20,6 +20,7 @@ struct SerialFcn {
         for (int k = 0; k < FIT_NPT; k++) chi2 += chi2_term(k, par, N, spl, knots, y[k], w[k]);
         return chi2;
     }
+    MG_DEFAULT_PAIR()
 };
 }  // namespace
 
