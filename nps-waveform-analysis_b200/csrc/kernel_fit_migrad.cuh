@@ -217,7 +217,7 @@ fit_migrad_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
 #define NPSWF_MT_THREADS 128
 #endif
 #ifndef NPSWF_MT_MINBLOCKS
-#define NPSWF_MT_MINBLOCKS 2
+#define NPSWF_MT_MINBLOCKS 4
 #endif
 #ifdef NPSWF_MT_FCN_INLINE
 #define MT_FCN_ATTR __forceinline__
@@ -227,102 +227,141 @@ fit_migrad_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
 constexpr int MT_THREADS = NPSWF_MT_THREADS;
 constexpr int MT_WTAB = 8192;        // |count| < MT_WTAB: a 12-bit ADC minus its pedestal stays far inside
 
+// the four coefficients of one spline interval (32 bytes, 32-byte aligned) in ONE request: sm_100's 256-bit load.  The
+// 32 lanes of a warp sit in different intervals, so every request is its own sector -- two 128-bit loads would put
+// twice as many sector requests through L1, which is what bounds this kernel.
+__device__ __forceinline__ void ldg_quad(const double *p, double &y, double &b, double &c, double &d)
+{
+    asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(y), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
+__device__ __forceinline__ int lds_s16(uint32_t addr)
+{
+    short v;
+    asm volatile("ld.shared.s16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return (int)v;
+}
+
+// chi2 of one fit at x, all 90 samples in order, one thread.  Out of line (Migrad calls it from ~20 places) with
+// everything it needs in argument registers; tile = shared-space address of this thread's column of counts.
+template <int N>
+__device__ __noinline__ double mt_chi2(uint32_t tile, const double *__restrict__ wtab, const double *__restrict__ spl, double lsb,
+                                       const double *__restrict__ x, int wlow, double w0)
+{
+    const double p0 = x[0];
+    double t[N], A[N];
+#pragma unroll
+    for (int n = 0; n < N; n++) { t[n] = x[1 + 2 * n]; A[n] = x[2 + 2 * n]; }
+    double chi2 = 0;
+#pragma unroll 2
+    for (int k = 0; k < mg::FIT_NPT; k++) {
+        const int c = lds_s16(tile + (uint32_t)k * (2u * MT_THREADS));
+        const double y = (double)c * lsb;
+        // |count| < wlow: Err is the constant floor sqrt(2.048)/4.096 (T2:952-954), the table entry is w0 -- most samples
+        // of a trace are pedestal, and the gather of 32 different table entries is 32 sector requests saved
+        const int ac = abs(c);
+        const double w = ac < wlow ? w0 : __ldg(wtab + ac);
+        const double xk = (double)(mg::FIT_X0 + k);
+        double val = p0;
+#pragma unroll
+        for (int n = 0; n < N; n++) {
+            const double dt0 = xk - t[n];
+            if (dt0 > 1 && dt0 < mg::FIT_T - 1) {   // T2:629
+                const int i = (int)dt0;
+                const double delx = dt0 - (double)i;
+                double q0, q1, q2, q3;
+                ldg_quad(spl + 4 * i, q0, q1, q2, q3);
+                val += A[n] * (q0 + delx * (q1 + delx * (q2 + delx * q3)));
+            }
+        }
+        const double tmp = (y - val) * w;
+        chi2 += tmp * tmp;
+    }
+    return chi2;
+}
+
+// chi2 at x with x[i] = vp and with x[i] = vm in ONE pass over the samples (every central difference of Migrad and
+// MnHesse): sample, weight and the spline terms of the untouched pulses are shared, each of the two sums is built
+// with exactly the operations of mt_chi2 in the same order, so the two values carry the same bits as two calls.
+template <int N>
+__device__ __noinline__ double2 mt_chi2_pair(uint32_t tile, const double *__restrict__ wtab, const double *__restrict__ spl,
+                                             double lsb, const double *__restrict__ x, int i, double vp, double vm, int wlow, double w0)
+{
+    double t[N], A[N];
+#pragma unroll
+    for (int n = 0; n < N; n++) { t[n] = x[1 + 2 * n]; A[n] = x[2 + 2 * n]; }
+    const bool ped = i == 0, is_t = (i & 1) != 0;
+    const int m = (i - 1) >> 1;                       // pulse of parameter i (i > 0): t_m = x[1+2m], A_m = x[2+2m]
+    const double p1 = ped ? vp : x[0], p2 = ped ? vm : x[0];
+    double c1 = 0, c2 = 0;
+#pragma unroll 2
+    for (int k = 0; k < mg::FIT_NPT; k++) {
+        const int c = lds_s16(tile + (uint32_t)k * (2u * MT_THREADS));
+        const double y = (double)c * lsb;
+        // |count| < wlow: Err is the constant floor sqrt(2.048)/4.096 (T2:952-954), the table entry is w0 -- most samples
+        // of a trace are pedestal, and the gather of 32 different table entries is 32 sector requests saved
+        const int ac = abs(c);
+        const double w = ac < wlow ? w0 : __ldg(wtab + ac);
+        const double xk = (double)(mg::FIT_X0 + k);
+        double v1 = p1, v2 = p2;
+#pragma unroll
+        for (int n = 0; n < N; n++) {
+            if (is_t && n == m) {                     // the pulse whose time is varied: two spline evaluations
+                const double d1 = xk - vp, d2 = xk - vm;
+                if (d1 > 1 && d1 < mg::FIT_T - 1) {
+                    const int j = (int)d1;
+                    const double delx = d1 - (double)j;
+                    double q0, q1, q2, q3;
+                    ldg_quad(spl + 4 * j, q0, q1, q2, q3);
+                    v1 += A[n] * (q0 + delx * (q1 + delx * (q2 + delx * q3)));
+                }
+                if (d2 > 1 && d2 < mg::FIT_T - 1) {
+                    const int j = (int)d2;
+                    const double delx = d2 - (double)j;
+                    double q0, q1, q2, q3;
+                    ldg_quad(spl + 4 * j, q0, q1, q2, q3);
+                    v2 += A[n] * (q0 + delx * (q1 + delx * (q2 + delx * q3)));
+                }
+            } else {
+                const double dt0 = xk - t[n];
+                if (dt0 > 1 && dt0 < mg::FIT_T - 1) {
+                    const int j = (int)dt0;
+                    const double delx = dt0 - (double)j;
+                    double q0, q1, q2, q3;
+                    ldg_quad(spl + 4 * j, q0, q1, q2, q3);
+                    const double sv = q0 + delx * (q1 + delx * (q2 + delx * q3));
+                    const bool amp = !ped && !is_t && n == m;     // the pulse whose amplitude is varied
+                    v1 += (amp ? vp : A[n]) * sv;
+                    v2 += (amp ? vm : A[n]) * sv;
+                }
+            }
+        }
+        const double r1 = (y - v1) * w, r2 = (y - v2) * w;
+        c1 += r1 * r1;
+        c2 += r2 * r2;
+    }
+    return make_double2(c1, c2);
+}
+
 template <int N>
 struct MgThreadFcn {
-    const int16_t *col;     // this thread's column of the shared count tile: sample k at col[k * MT_THREADS]
+    uint32_t tile;          // shared-space address of this thread's column of the count tile: sample k at tile + k * 2 * MT_THREADS
     const double *wtab;     // inverse error by |count|
     const double *spl;
-    double lsb;
+    double lsb, w0;
+    int wlow;
     int ncalls;
-    __device__ MT_FCN_ATTR double operator()(const double *x)
+    __device__ __forceinline__ double operator()(const double *x)
     {
         ncalls++;
-        const double p0 = x[0];
-        double t[N], A[N];
-#pragma unroll
-        for (int n = 0; n < N; n++) { t[n] = x[1 + 2 * n]; A[n] = x[2 + 2 * n]; }
-        double chi2 = 0;
-#pragma unroll 2
-        for (int k = 0; k < mg::FIT_NPT; k++) {
-            const int c = col[k * MT_THREADS];
-            const double y = (double)c * lsb;
-            const double w = __ldg(wtab + abs(c));
-            const double xk = (double)(mg::FIT_X0 + k);
-            double val = p0;
-#pragma unroll
-            for (int n = 0; n < N; n++) {
-                const double dt0 = xk - t[n];
-                if (dt0 > 1 && dt0 < mg::FIT_T - 1) {   // T2:629
-                    const int i = (int)dt0;
-                    const double delx = dt0 - (double)i;
-                    const double2 c01 = __ldg(reinterpret_cast<const double2 *>(spl + 4 * i));
-                    const double2 c23 = __ldg(reinterpret_cast<const double2 *>(spl + 4 * i) + 1);
-                    val += A[n] * (c01.x + delx * (c01.y + delx * (c23.x + delx * c23.y)));
-                }
-            }
-            const double tmp = (y - val) * w;
-            chi2 += tmp * tmp;
-        }
-        return chi2;
+        return mt_chi2<N>(tile, wtab, spl, lsb, x, wlow, w0);
     }
-    // chi2 at x with x[i] = vp and with x[i] = vm in ONE pass over the samples (every central difference of Migrad and
-    // MnHesse): sample, weight and the spline terms of the untouched pulses are shared, each of the two sums is built
-    // with exactly the operations of operator() in the same order, so f1 and f2 carry the same bits as two calls.
-    __device__ MT_FCN_ATTR void pair(double *x, int i, double vp, double vm, double &f1, double &f2)
+    __device__ __forceinline__ void pair(double *x, int i, double vp, double vm, double &f1, double &f2)
     {
         ncalls += 2;
-        double t[N], A[N];
-#pragma unroll
-        for (int n = 0; n < N; n++) { t[n] = x[1 + 2 * n]; A[n] = x[2 + 2 * n]; }
-        const bool ped = i == 0, is_t = (i & 1) != 0;
-        const int m = (i - 1) >> 1;                       // pulse of parameter i (i > 0): t_m = x[1+2m], A_m = x[2+2m]
-        const double p1 = ped ? vp : x[0], p2 = ped ? vm : x[0];
-        double c1 = 0, c2 = 0;
-#pragma unroll 2
-        for (int k = 0; k < mg::FIT_NPT; k++) {
-            const int c = col[k * MT_THREADS];
-            const double y = (double)c * lsb;
-            const double w = __ldg(wtab + abs(c));
-            const double xk = (double)(mg::FIT_X0 + k);
-            double v1 = p1, v2 = p2;
-#pragma unroll
-            for (int n = 0; n < N; n++) {
-                if (is_t && n == m) {                     // the pulse whose time is varied: two spline evaluations
-                    const double d1 = xk - vp, d2 = xk - vm;
-                    if (d1 > 1 && d1 < mg::FIT_T - 1) {
-                        const int j = (int)d1;
-                        const double delx = d1 - (double)j;
-                        const double2 c01 = __ldg(reinterpret_cast<const double2 *>(spl + 4 * j));
-                        const double2 c23 = __ldg(reinterpret_cast<const double2 *>(spl + 4 * j) + 1);
-                        v1 += A[n] * (c01.x + delx * (c01.y + delx * (c23.x + delx * c23.y)));
-                    }
-                    if (d2 > 1 && d2 < mg::FIT_T - 1) {
-                        const int j = (int)d2;
-                        const double delx = d2 - (double)j;
-                        const double2 c01 = __ldg(reinterpret_cast<const double2 *>(spl + 4 * j));
-                        const double2 c23 = __ldg(reinterpret_cast<const double2 *>(spl + 4 * j) + 1);
-                        v2 += A[n] * (c01.x + delx * (c01.y + delx * (c23.x + delx * c23.y)));
-                    }
-                } else {
-                    const double dt0 = xk - t[n];
-                    if (dt0 > 1 && dt0 < mg::FIT_T - 1) {
-                        const int j = (int)dt0;
-                        const double delx = dt0 - (double)j;
-                        const double2 c01 = __ldg(reinterpret_cast<const double2 *>(spl + 4 * j));
-                        const double2 c23 = __ldg(reinterpret_cast<const double2 *>(spl + 4 * j) + 1);
-                        const double sv = c01.x + delx * (c01.y + delx * (c23.x + delx * c23.y));
-                        const bool amp = !ped && !is_t && n == m;     // the pulse whose amplitude is varied
-                        v1 += (amp ? vp : A[n]) * sv;
-                        v2 += (amp ? vm : A[n]) * sv;
-                    }
-                }
-            }
-            const double r1 = (y - v1) * w, r2 = (y - v2) * w;
-            c1 += r1 * r1;
-            c2 += r2 * r2;
-        }
-        f1 = c1;
-        f2 = c2;
+        const double2 r = mt_chi2_pair<N>(tile, wtab, spl, lsb, x, i, vp, vm, wlow, w0);
+        f1 = r.x;
+        f2 = r.y;
     }
 };
 
@@ -338,7 +377,7 @@ fit_migrad_thread_kernel(const int *__restrict__ job_list, const int *__restrict
                          const double *__restrict__ signal, const double *__restrict__ corr_time_HMS, DevCalib cal, KParams kp,
                          double *__restrict__ wftime, double *__restrict__ wfampl, double *__restrict__ chi2_out,
                          double *__restrict__ timewf, double *__restrict__ amplwf, uint8_t *__restrict__ status,
-                         DeviceCounters *__restrict__ ctr, const double *__restrict__ wtab, double lsb,
+                         DeviceCounters *__restrict__ ctr, const double *__restrict__ wtab, double lsb, int wlow,
                          int *__restrict__ ho_count, int *__restrict__ ho_list)
 {
     constexpr int P = 2 * N + 1;
@@ -373,8 +412,8 @@ fit_migrad_thread_kernel(const int *__restrict__ job_list, const int *__restrict
                 ho_list[atomicAdd(ho_count, 1)] = raw;
             } else {
                 MgThreadFcn<N> fcn;
-                fcn.col = tile + threadIdx.x; fcn.wtab = wtab; fcn.spl = cal.spline + (size_t)bn * (T - 1) * 4;
-                fcn.lsb = lsb; fcn.ncalls = 0;
+                fcn.tile = smem_u32(tile + threadIdx.x); fcn.wtab = wtab; fcn.spl = cal.spline + (size_t)bn * (T - 1) * 4;
+                fcn.lsb = lsb; fcn.ncalls = 0; fcn.wlow = wlow; fcn.w0 = __ldg(wtab);
                 const double tref = cal.timeref[bn];
                 double *wt = wftime + (size_t)item * MAXP, *wa = wfampl + (size_t)item * MAXP;
                 mg::fit_seeds(sig, tref, wt, wa, N, start);

@@ -19,6 +19,7 @@ struct MigradArgs {
     // thread-per-fit kernel only: inverse-error table by |count|, the ADC step, the hand-over list for traces off the lattice
     const double *wtab = nullptr;
     double lsb = 0;
+    int wlow = 0;             // table entries below this index all hold the constant-error weight
     int *ho_count = nullptr, *ho_list = nullptr;
 };
 
@@ -32,5 +33,6 @@ constexpr int MIGRAD_WTAB_ENTRIES = 8192;
 cudaError_t migrad_thread_setup(int occ[4]);
 cudaError_t migrad_thread_launch(int N, int grid, cudaStream_t st, const MigradArgs &a);
 cudaError_t migrad_build_wtab(double *d_wtab, double lsb, cudaStream_t st);
+int migrad_wtab_floor(double lsb);   // first |count| whose error is above the constant floor of T2:952-954
 
 }  // namespace npswf

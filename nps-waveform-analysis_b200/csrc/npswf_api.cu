@@ -84,6 +84,7 @@ struct DevSlot {
     int occ_migrad_thread[4] = {0, 4, 4, 4};   // fit_migrad_thread_kernel<1, 2, 3>
     double *mg_wtab = nullptr;       // inverse error by |ADC count| (thread-per-fit Migrad kernels)
     double mg_wtab_lsb = 0;          // the ADC step the table was built for
+    int mg_wlow = 0;                 // entries below this index hold the constant-error weight
     std::vector<int> local_cpus;     // cores of the NUMA node the GPU hangs off (within this process's affinity mask); empty = unknown
     cudaEvent_t last_use = nullptr;  // end of the last device-path call: later calls order themselves behind it (shared scratch, job lists, fit streams)
     bool last_use_valid = false;
@@ -492,12 +493,13 @@ int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, cons
                 if (s.mg_wtab_lsb != h->pack_lsb) {   // (re)built on the stream that uses it first; later users are ordered behind it by the fork
                     CU_TRY(h, migrad_build_wtab(s.mg_wtab, h->pack_lsb, caller));
                     s.mg_wtab_lsb = h->pack_lsb;
+                    s.mg_wlow = migrad_wtab_floor(h->pack_lsb);
                     if (conc) {
                         CU_TRY(h, cudaEventRecord(s.fit_fork, caller));
                         for (int i = 0; i < 4; i++) CU_TRY(h, cudaStreamWaitEvent(s.fit_stream[i], s.fit_fork, 0));
                     }
                 }
-                ma.wtab = s.mg_wtab; ma.lsb = h->pack_lsb;
+                ma.wtab = s.mg_wtab; ma.lsb = h->pack_lsb; ma.wlow = s.mg_wlow;
                 ma.ho_count = w.fit_count + 32 + N;
                 ma.ho_list = w.cont_list + (size_t)(N - 1) * stride;
                 CU_TRY(h, migrad_thread_launch(N, s.sm_count * s.occ_migrad_thread[N], st, ma));
@@ -931,6 +933,8 @@ int analyze_range_impl(npswf_handle *h, int d, int64_t lo, int64_t hi, const Hos
         // compute: after the upload, and not before chunk k - 2 is done (two chunks in flight)
         CU_TRY(h, cudaStreamWaitEvent(s_cmp, w.ev_in, 0));
         if (k >= 2) CU_TRY(h, cudaStreamWaitEvent(s_cmp, s.ws[(which + 1) % 3].ev_cmp, 0));
+        if (k >= 1 && h->fit_mode == NPSWF_FIT_MIGRAD)   // Migrad kernels: one chunk computing at a time (see the device path)
+            CU_TRY(h, cudaStreamWaitEvent(s_cmp, s.ws[(which + 2) % 3].ev_cmp, 0));
         if (io.packed) {
             unpack_kernel<<<(unsigned)std::min<int64_t>(n, 4 * s.sm_count), UNPACK_THREADS, 0, s_cmp>>>(
                 w.packed, w.poffs, (long long)io.offsets[e0], n, w.signal, w.pres);
@@ -1626,7 +1630,9 @@ int npswf_analyze_batch_device(npswf_handle *h, int32_t dev_slot, int64_t n_even
         chunk = std::min<int64_t>(h->dev_cap, std::max<int64_t>(h->chunk, ((n_events + 1) / 2 + 147) / 148 * 148));
         if ((rc = grow_scratch(h, s, chunk))) return rc;
     }
-    const bool overlap = !h->profiling && n_events > chunk;
+    // (the Migrad kernels are long-running persistent grids that fill the device on their own: two chunks' worth of
+    // them co-scheduled run 20-50 % slower than one after the other, so that mode keeps its chunks in sequence)
+    const bool overlap = !h->profiling && n_events > chunk && h->fit_mode != NPSWF_FIT_MIGRAD;
     if (overlap) {
         CU_TRY(h, cudaEventRecord(s.fit_fork, st));
         for (int i = 0; i < 2; i++) CU_TRY(h, cudaStreamWaitEvent(s.ws[i].stream, s.fit_fork, 0));

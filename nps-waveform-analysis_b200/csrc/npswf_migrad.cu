@@ -54,7 +54,7 @@ static void launch_thread(int grid, cudaStream_t st, const MigradArgs &a)
 {
     fit_migrad_thread_kernel<N><<<grid, MT_THREADS, 0, st>>>(a.job_list, a.job_count, a.job_next, a.signal, a.corr, a.cal, a.kp,
                                                             a.wftime, a.wfampl, a.chi2, a.timewf, a.amplwf, a.status, a.ctr,
-                                                            a.wtab, a.lsb, a.ho_count, a.ho_list);
+                                                            a.wtab, a.lsb, a.wlow, a.ho_count, a.ho_list);
 }
 
 cudaError_t migrad_thread_launch(int N, int grid, cudaStream_t st, const MigradArgs &a)
@@ -64,6 +64,14 @@ cudaError_t migrad_thread_launch(int N, int grid, cudaStream_t st, const MigradA
     else if (N == 2) launch_thread<2>(grid, st, a);
     else launch_thread<3>(grid, st, a);
     return cudaGetLastError();
+}
+
+int migrad_wtab_floor(double lsb)
+{
+    const double w0 = mg::inv_err(0.0);
+    int c = 0;
+    while (c < MT_WTAB && mg::inv_err((double)c * lsb) == w0) c++;
+    return c;
 }
 
 cudaError_t migrad_build_wtab(double *d_wtab, double lsb, cudaStream_t st)

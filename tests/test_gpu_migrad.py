@@ -189,3 +189,51 @@ def test_general_interpx_knots(pkg, calib, spline):
     bad["interpX"] = cal["interpX"] + 2.0            # starts at 2: does not cover the guard interval
     with pytest.raises(pkg.NpsWfError):
         pkg.NpsWf(bad)
+
+
+def test_migrad_mode_many_pulses(pkg, calib, orc):
+    """7..12 pulses per block (P = 15..25 parameters: the 25-parameter instance of the warp-per-fit kernel, Migrad's
+    call limit 1000 + 100 P + 5 P^2, MnHesse on a 25 x 25 matrix): driven through the stage-level Fitwf entry point with
+    explicit seeds, every fit compared with the oracle's -- verdict, times, amplitudes, chi2 -- bit for bit."""
+    rng = np.random.default_rng(21)
+    n_blocks = 48
+    sig = np.zeros((1, 1080, 110))
+    npulse = np.zeros((1, 1080), np.int32)
+    t = np.full((1, 1080, 12), -999.0)
+    a = np.full((1, 1080, 12), -999.0)
+    mask = np.zeros((1, 1080), np.uint8)
+    blocks = rng.choice(1080, n_blocks, replace=False)
+    for j, b in enumerate(blocks):
+        N = 7 + j % 6
+        shape = calib["interpY"][b]
+        peak = int(np.argmax(shape))
+        pos = np.sort(rng.choice(np.arange(14, 96, 6), N, replace=False)) + rng.integers(0, 3, N)
+        trace = rng.normal(0.0, 0.3, 110)
+        for p in pos:
+            amp = rng.uniform(4.0, 40.0)
+            sh = np.zeros(110)
+            d = int(p) - peak
+            if d >= 0:
+                sh[d:] = shape[:110 - d]
+            else:
+                sh[:110 + d] = shape[-d:]
+            trace += amp * sh
+        sig[0, b] = np.round(trace / synth.LSB) * synth.LSB
+        npulse[0, b] = N
+        t[0, b, :N] = pos + rng.choice([-0.5, 0.5], N)                 # TSpectrum-like half-integer seeds
+        a[0, b, :N] = np.abs(sig[0, b, pos] - sig[0, b].min())
+        mask[0, b] = 1
+    hm = pkg.NpsWf(calib, fit_mode=pkg.FIT_MIGRAD)
+    corr = np.array([1.25])
+    r = hm.Fitwf(sig, corr, mask, npulse, t, a)
+    verdicts = {4: 0, 8: 0, 16: 0}
+    for b in blocks:
+        N = int(npulse[0, b])
+        o = orc.fitwf(b, sig[0], N, t[0, b], a[0, b], corr[0])
+        assert (r["status"][0, b] & 28) == o["status"], (b, N, r["status"][0, b], o["status"])
+        assert np.array_equal(r["wftime"][0, b, :N], o["wftime"][:N]), (b, N)
+        assert np.array_equal(r["wfampl"][0, b, :N], o["wfampl"][:N]), (b, N)
+        assert r["chi2"][0, b] == o["chi2"], (b, N)
+        verdicts[o["status"]] += 1
+    print("7-12 pulse fits identical to the oracle: ok %d, ok on retry %d, fall-back %d" % (verdicts[4], verdicts[8], verdicts[16]))
+    assert verdicts[4] + verdicts[8] > 0
