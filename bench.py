@@ -365,6 +365,34 @@ def main():
                            "bytes_per_block_waveform": (h2d_i16 + d2h_flat) / float(Ee * NB),
                            "input": "npswf_analyze_batch_flat_i16: int16 counts in, pulses packed on the device out"}
 
+    # ---- one process, all GPUs: the handle's own event sharding (n_devices = N, one host thread per device inside the
+    # call) instead of one process per GPU, same transport as i16_flat.  Rank 0 runs it while the other ranks wait.
+    if not args.no_e2e and world > 1:
+        barrier()
+        if rank == 0:
+            hN = pkg.NpsWf(cal, devices=list(range(world)))
+            EN = Ee * world
+            hkN = pkg.pinned_empty((EN, NB, NT), np.int16)
+            hpN = pkg.pinned_empty((EN, NB), np.int32)
+            hcN = pkg.pinned_empty((EN,), np.float64)
+            for r in range(world):
+                hkN[r * Ee:(r + 1) * Ee] = hk
+                hpN[r * Ee:(r + 1) * Ee] = hp
+                hcN[r * Ee:(r + 1) * Ee] = hc
+            hfN = hN.alloc_flat_outputs(EN, EN * NB * 4, pinned=True)
+            hN.analyze_flat_i16(hkN, synth.LSB, hpN, hcN, out=hfN)
+            hN.reset_counters()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                hN.analyze_flat_i16(hkN, synth.LSB, hpN, hcN, out=hfN)
+            dtN = time.perf_counter() - t0
+            e2e["in_process_all_gpus"] = {"value": hN.counters()["n_fit_attempted"] / dtN, "unit": UNIT, "ms_per_step": 1e3 * dtN / 3,
+                                          "events_per_step": EN,
+                                          "input": "ONE process, handle with n_devices = %d (contiguous event ranges, one host thread per "
+                                                   "device inside npswf_analyze_batch_flat_i16), int16 in / flat out" % world}
+            del hN, hkN, hpN, hcN, hfN
+        barrier()
+
     # ---- the MIGRAD fit mode (the reference's own minimiser on the device; outputs bit-identical to the oracle): the
     # same resident batches and the same host call, fewer steps (a step takes ~10x longer)
     if args.migrad_steps > 0:
@@ -432,15 +460,15 @@ def main():
                          "units_per_s": stage_units[k] / (ms * 1e-3) if ms > 0 else 0.0}
     dom = max(("front", "search", "fit"), key=lambda k: stages[k + "_ms"])
     launches_per_chunk = {"front": 1, "search": 1, "fit": 14}
-    # dram__bytes_read.sum + dram__bytes_write.sum per block-waveform, from the `ncu --set full` capture of this build
-    # (profiles/r1_ncu_full_final6.csv: launches of 1 184 events = 1 278 720 block-waveforms)
-    ncu_traffic_per_unit = {"front": (1.133616e9 + 538.668e6) / 1278720.0, "search": (1.799080e9 + 291.132e6) / 1278720.0}
+    # dram__bytes_read.sum + dram__bytes_write.sum per block-waveform, from the `ncu --set full` capture of this round's
+    # build (profiles/r2_ncu_full_search_front.csv: launches of 1 184 events = 1 278 720 block-waveforms)
+    ncu_traffic_per_unit = {"front": (1.132483e9 + 539.487e6) / 1278720.0, "search": (1.799129e9 + 292.069e6) / 1278720.0}
     units_per_launch = units_local / chunks
     traffic = ncu_traffic_per_unit[dom] * units_per_launch if dom in ncu_traffic_per_unit else None
     roofline = {"kernel": {"front": "front_kernel", "search": "search_kernel", "fit": "fit_thread_kernel<1,2> + fit_small_kernel + fit_kernel<25> (14 launches)"}[dom],
                 "bound": "hbm", "achieved": stage_rows[dom]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
                 "frac": stage_rows[dom]["achieved_gbs"] / hbm, "traffic": traffic,
-                "traffic_source": "ncu --set full, profiles/r1_ncu_full_final6.csv (bytes per block-waveform x block-waveforms per launch)",
+                "traffic_source": "ncu --set full, profiles/r2_ncu_full_search_front.csv (bytes per block-waveform x block-waveforms per launch)",
                 "peak_source": peak_src,
                 "note": "dominant stage is FP64-pipe bound, not HBM bound (bit-faithful FP64 TSpectrum / FP64 LM); "
                         "see stages, fp64_peak_gflops_measured and DESIGN.md",
