@@ -9,6 +9,8 @@
  * Conventions: plain pointers and sizes only; caller owns every host buffer; return 0 = ok,
  * < 0 = error (message via npswf_last_error); nothing throws across the boundary; a handle is
  * used by one host thread at a time; host-buffer calls are synchronous w.r.t. their outputs.
+ * Calls on a handle share its device scratch: the library orders them itself (a device-path call
+ * leaves an event behind that the next call -- on any stream, device or host path -- waits for).
  * There is NO CPU fallback: every compute entry point fails with NPSWF_ERR_CUDA when no
  * sm_100 device is usable.
  */
