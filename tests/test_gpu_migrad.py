@@ -237,3 +237,34 @@ def test_migrad_mode_many_pulses(pkg, calib, orc):
         verdicts[o["status"]] += 1
     print("7-12 pulse fits identical to the oracle: ok %d, ok on retry %d, fall-back %d" % (verdicts[4], verdicts[8], verdicts[16]))
     assert verdicts[4] + verdicts[8] > 0
+
+
+def test_migrad_mode_through_every_entry_point(pkg, calib, spline):
+    """MIGRAD mode behind the other transports and layouts: int16 counts, packed hcana stream (device unpack), flat
+    outputs, blocks without a reference waveform (preswf = 0) -- all equal to the oracle / to the plain call, bit for bit."""
+    threads = os.cpu_count() or 1
+    cal = dict(calib)
+    preswf = np.ones(1080, np.int32)
+    preswf[np.random.default_rng(6).choice(1080, 40, replace=False)] = 0
+    cal["preswf"] = preswf
+    orc = oracle.Oracle(cal)
+    ev = synth.generate_host(synth.config_params(2, absent_frac=0.03), spline, calib, 44_000_000, 12, n_threads=threads, counts=True)
+    ref = orc.analyze_batch(ev["signal"], ev["pres"], ev["corr_time_HMS"], n_threads=threads)
+    h = pkg.NpsWf(cal, fit_mode=pkg.FIT_MIGRAD, chunk_events=5)      # several ragged chunks per call
+    a = h.analyze(ev["signal"], ev["pres"], ev["corr_time_HMS"])
+    for k in ("wfnpulse", "status", "wftime", "wfampl", "chi2", "timewf", "amplwf"):
+        assert np.array_equal(a[k], ref[k]), k
+    b = h.analyze_i16(ev["counts"], synth.LSB, ev["pres"], ev["corr_time_HMS"])
+    samp, offs = synth.pack_events(ev["signal"], ev["pres"], seed=3)
+    c = h.analyze_packed(samp, offs, ev["corr_time_HMS"])
+    for k in a:
+        assert np.array_equal(a[k], b[k]), ("i16", k)
+        assert np.array_equal(a[k], c[k]), ("packed", k)
+    f = h.analyze_flat_i16(ev["counts"], synth.LSB, ev["pres"], ev["corr_time_HMS"])
+    assert f["n_pulses"] == int(a["wfnpulse"].sum())
+    for e in range(12):
+        ft, fa, _ = pkg.flatten_event(a["wfnpulse"][e], a["wftime"][e], a["wfampl"][e])
+        o, n = int(f["pulse_offset"][e]), int(f["pulse_count"][e])
+        assert n == len(ft) and np.array_equal(f["wftime_pool"][o:o + n], ft) and np.array_equal(f["wfampl_pool"][o:o + n], fa)
+    for k in ("chi2", "timewf", "amplwf", "status"):
+        assert np.array_equal(f[k], a[k]), ("flat", k)
