@@ -172,7 +172,7 @@ class Oracle:
 
     def mf_calib(self):
         y = np.zeros((NBLOCKS, MFW)); i = np.zeros(NBLOCKS)
-        lib().oracle_get_mf(self.h, _p(y), _p(i))
+        self._lib.oracle_get_mf(self.h, _p(y), _p(i))
         return y, i
 
     def spline_coeffs(self):
@@ -180,19 +180,19 @@ class Oracle:
         out = np.zeros((NBLOCKS, NTIME - 1, 4))
         y = np.zeros(NTIME - 1); b = np.zeros(NTIME - 1); c = np.zeros(NTIME - 1); d = np.zeros(NTIME - 1)
         for bn in range(NBLOCKS):
-            lib().oracle_get_spline(self.h, C.c_int(bn), _p(y), _p(b), _p(c), _p(d))
+            self._lib.oracle_get_spline(self.h, C.c_int(bn), _p(y), _p(b), _p(c), _p(d))
             out[bn, :, 0] = y; out[bn, :, 1] = b; out[bn, :, 2] = c; out[bn, :, 3] = d
         return out
 
     def spline_eval(self, bn, x):
-        return np.array([lib().oracle_spline_eval(self.h, int(bn), float(v)) for v in np.atleast_1d(x)])
+        return np.array([self._lib.oracle_spline_eval(self.h, int(bn), float(v)) for v in np.atleast_1d(x)])
 
     def matched_filter(self, bn, signal_event, minsignal=None):
         sig = _c(signal_event, np.float64).reshape(NBLOCKS, NTIME)
         if minsignal is None:
             minsignal = min(1e6, sig[bn].min())
         mf = np.zeros(NTIME); hist = np.zeros(NTIME, np.float32)
-        lib().oracle_matched_filter(self.h, C.c_int(bn), _p(sig), C.c_double(minsignal), _p(mf), _p(hist))
+        self._lib.oracle_matched_filter(self.h, C.c_int(bn), _p(sig), C.c_double(minsignal), _p(mf), _p(hist))
         return mf, hist
 
     def find_pulses_mf(self, bn, signal_event, pres, minsignal=None):
@@ -201,22 +201,22 @@ class Oracle:
         if minsignal is None:
             minsignal = min(1e6, sig[bn].min())
         t = np.full(MAXP, -999.0); a = np.full(MAXP, -999.0)
-        lib().oracle_find_pulses_mf.restype = C.c_int
-        n = lib().oracle_find_pulses_mf(self.h, C.c_int(bn), _p(sig), _p(pr), C.c_double(minsignal), _p(t), _p(a))
+        self._lib.oracle_find_pulses_mf.restype = C.c_int
+        n = self._lib.oracle_find_pulses_mf(self.h, C.c_int(bn), _p(sig), _p(pr), C.c_double(minsignal), _p(t), _p(a))
         return n, t, a
 
     def pass_cluster_threshold(self, bn, signal_event, pres):
         sig = _c(signal_event, np.float64).reshape(NBLOCKS, NTIME)
         pr = _c(pres, np.int32)
-        lib().oracle_pass_cluster_threshold.restype = C.c_int
-        return bool(lib().oracle_pass_cluster_threshold(self.h, C.c_int(bn), _p(sig), _p(pr)))
+        self._lib.oracle_pass_cluster_threshold.restype = C.c_int
+        return bool(self._lib.oracle_pass_cluster_threshold(self.h, C.c_int(bn), _p(sig), _p(pr)))
 
     def fitwf(self, bn, signal_event, npulse, wftime, wfampl, corr_time_HMS=0.0):
         sig = _c(signal_event, np.float64).reshape(NBLOCKS, NTIME)
         t = _c(wftime, np.float64).copy(); a = _c(wfampl, np.float64).copy()
         chi2 = C.c_double(); nc = C.c_int32(); raw = np.zeros(25)
-        lib().oracle_fitwf.restype = C.c_int
-        st = lib().oracle_fitwf(self.h, C.c_int(bn), _p(sig), C.c_int(npulse), C.c_double(corr_time_HMS),
+        self._lib.oracle_fitwf.restype = C.c_int
+        st = self._lib.oracle_fitwf(self.h, C.c_int(bn), _p(sig), C.c_int(npulse), C.c_double(corr_time_HMS),
                                 _p(t), _p(a), C.byref(chi2), C.byref(nc), _p(raw))
         return dict(status=st, wftime=t, wfampl=a, chi2=chi2.value, ncalls=nc.value, params=raw[:2 * npulse + 1])
 
@@ -225,8 +225,8 @@ class Oracle:
         sig = _c(signal_event, np.float64).reshape(NBLOCKS, NTIME)
         pr = _c(pres, np.int32)
         h1 = np.zeros(NBLOCKS * MAXP); h2 = np.zeros(NBLOCKS * MAXP)
-        lib().oracle_event_times.restype = C.c_int
-        n = lib().oracle_event_times(self.h, _p(sig), _p(pr), C.c_double(corr_time_HMS), _p(h1), _p(h2))
+        self._lib.oracle_event_times.restype = C.c_int
+        n = self._lib.oracle_event_times(self.h, _p(sig), _p(pr), C.c_double(corr_time_HMS), _p(h1), _p(h2))
         return h1[:n].copy(), h2[:n].copy()
 
     def find_pulses_batch(self, signal, pres, n_threads=1):
@@ -248,7 +248,7 @@ class Oracle:
             wfampl=np.zeros((E, NBLOCKS, MAXP)), chi2=np.zeros((E, NBLOCKS)), timewf=np.zeros((E, NBLOCKS)),
             amplwf=np.zeros((E, NBLOCKS)), status=np.zeros((E, NBLOCKS), np.uint8),
             ncalls=np.zeros((E, NBLOCKS), np.int32))
-        lib().oracle_analyze_batch(self.h, C.c_int64(E), _p(sig), _p(pr), _p(co), _p(out["wfnpulse"]),
+        self._lib.oracle_analyze_batch(self.h, C.c_int64(E), _p(sig), _p(pr), _p(co), _p(out["wfnpulse"]),
                                    _p(out["wftime"]), _p(out["wfampl"]), _p(out["chi2"]), _p(out["timewf"]),
                                    _p(out["amplwf"]), _p(out["status"]), _p(out["ncalls"]), C.c_int(n_threads))
         return out
