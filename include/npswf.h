@@ -68,10 +68,14 @@ typedef struct NpsWfConfig {
  *   from the same seeds, EDM goal 2e-5, call limit 1000+100P+5P^2 -- re-implemented for the device
  *   (csrc/migrad_core.hpp, fit_migrad_kernel) in the reference's FMA-free arithmetic and summation order: fitted
  *   values, chi2 and the ok / retry / fall-back verdict follow Migrad's path.
+ * NPSWF_FIT_VM: Migrad's recursion (seed from the second derivatives, MnLineSearch, Davidon update, EDM stop) with
+ *   ANALYTIC gradients instead of Minuit's numerical ones and no MnHesse (fit_vm_thread_kernel, 1-3 pulses; fits that
+ *   leave the common path go through the exact kernels): it follows Migrad into the same minimum and stops where
+ *   Migrad stops on ~99.98 % of ordinary fits, at a third of MIGRAD's cost; 4+ pulses run through the exact kernels.
  * NPSWF_FIT_FAST: Levenberg-Marquardt on analytic spline derivatives (fit_thread_kernel & co.), ~10x cheaper; it
  *   converges the same chi2 tighter than Migrad's EDM goal, and where the chi2 has several local minima it may end
  *   in another one than Migrad does. */
-enum { NPSWF_FIT_FAST = 0, NPSWF_FIT_MIGRAD = 1 };
+enum { NPSWF_FIT_FAST = 0, NPSWF_FIT_MIGRAD = 1, NPSWF_FIT_VM = 2 };
 
 /* The calibration globals of T2:74-85 as loaded at T2:360-469.  mfyref / mfint are derived
  * inside npswf_create exactly as T2:440-451 does. */
@@ -181,6 +185,11 @@ int npswf_hcana_pulses(int32_t n_adc, const double *adcCounter, const double *ad
  * that many doubles (either may be NULL).  cortime: the calibration's [NBLOCKS] Float_t; dt: ns per sample. */
 int64_t npswf_event_times(const int32_t *wfnpulse, const double *wftime_padded, const double *wfampl_padded, const uint8_t *status,
                           const float *cortime, double dt, double *h1time, double *h2time);
+
+/* Diagnostics of the NPSWF_FIT_VM mode: how many fits left fit_vm_thread_kernel for the exact Migrad kernels, by reason
+ * (0 evaluation limit or trace not exact in binary32, 1 second derivative <= 0 at the seeds, 2 EDM negative / not a
+ * number, 3 above the EDM limit, 4 not a descent direction), since the last reset (device 0). */
+int npswf_debug_vm_reasons(npswf_handle *h, uint64_t out[8], int reset);
 
 /* Measured rate of the raw binary64 uploads out of the caller's pinned buffers (CUDA events around the raw part of a
  * chunk, running mean over the devices; 48 until something was measured), and the number of host cores the packer

@@ -22,7 +22,7 @@ LIB_PATH = os.environ.get("NPSWF_LIB") or os.path.join(_HERE, "lib", "libnpswf.s
 NTIME, NCOL, NLIN, NBLOCKS, MAXWFPULSES, MFWIDTH = 110, 30, 36, 1080, 12, 11
 ST_PRESENT, ST_OKTOFIT, ST_FIT_OK1, ST_FIT_OK2, ST_FALLBACK = 1, 2, 4, 8, 16
 ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_CALIB = -1, -2, -3, -4
-FIT_FAST, FIT_MIGRAD = 0, 1
+FIT_FAST, FIT_MIGRAD, FIT_VM = 0, 1, 2
 
 
 class NpsWfError(RuntimeError):
@@ -58,7 +58,7 @@ EXPORTS = [
     "npswf_device_timeref", "npswf_flatten_event", "npswf_debug_exp", "npswf_debug_exact_ops", "npswf_debug_fp64_peak", "npswf_unpack_batch", "npswf_analyze_batch_packed",
     "npswf_event_diagnostics_batch", "npswf_event_diagnostics_device", "npswf_set_profiling",
     "npswf_get_stage_times", "npswf_set_host_packing", "npswf_host_packing_stats", "npswf_debug_pack_counts", "npswf_analyze_batch_flat",
-    "npswf_analyze_batch_flat_i16", "npswf_host_upload_rate", "npswf_hcana_pulses", "npswf_event_times",
+    "npswf_analyze_batch_flat_i16", "npswf_host_upload_rate", "npswf_hcana_pulses", "npswf_event_times", "npswf_debug_vm_reasons",
 ]
 
 _lib = None
@@ -244,6 +244,12 @@ class NpsWf:
         a, b, r, n = C.c_int64(), C.c_int64(), C.c_double(), C.c_int64()
         self._check(lib().npswf_host_packing_stats(self.h, C.byref(a), C.byref(b), C.byref(r), C.byref(n)))
         return dict(packed_chunks=a.value, raw_chunks=b.value, pack_gb_per_s=r.value, packed_input_bytes=n.value)
+
+    def vm_reasons(self, reset=True):
+        """NPSWF_FIT_VM diagnostics: fits handed to the exact Migrad kernels, by reason (see npswf.h)."""
+        out = np.zeros(8, np.uint64)
+        self._check(lib().npswf_debug_vm_reasons(self.h, _p(out), C.c_int(1 if reset else 0)))
+        return [int(v) for v in out]
 
     def host_upload_rate(self):
         """(measured GB/s of the raw binary64 uploads, host cores the transport threads are bound to)."""

@@ -351,14 +351,22 @@ struct MgThreadFcn {
     double lsb, w0;
     int wlow;
     int ncalls;
+    // A thread's fit is as slow as 32 fits: one that needs far more evaluations than usual (call limit, the strategy-2
+    // retry) would hold its warp -- and, at the end of a short job list, the whole kernel -- for tens of milliseconds.
+    // Past `cap` evaluations the functor answers NaN, which ends every loop of the minimiser at once, and the fit is
+    // handed to the warp-per-fit kernel, which runs it again from its seeds (same result, a fraction of the latency).
+    int cap;
+    bool aborted;
     __device__ __forceinline__ double operator()(const double *x)
     {
         ncalls++;
+        if (ncalls > cap) { aborted = true; return __longlong_as_double(0x7ff8000000000000LL); }
         return mt_chi2<N>(tile, wtab, spl, lsb, x, wlow, w0);
     }
     __device__ __forceinline__ void pair(double *x, int i, double vp, double vm, double &f1, double &f2)
     {
         ncalls += 2;
+        if (ncalls > cap) { aborted = true; f1 = f2 = __longlong_as_double(0x7ff8000000000000LL); return; }
         const double2 r = mt_chi2_pair<N>(tile, wtab, spl, lsb, x, i, vp, vm, wlow, w0);
         f1 = r.x;
         f2 = r.y;
@@ -395,6 +403,7 @@ fit_migrad_thread_kernel(const int *__restrict__ job_list, const int *__restrict
         if (base >= njobs) break;
         const int job = base + lane;
         if (job < njobs) {
+            bool continue_next = false;
             const int raw = job_list[job];
             const long long item = (long long)(raw & (FIT_CONT_RESTART - 1));
             const long long e = item / B;
@@ -414,10 +423,20 @@ fit_migrad_thread_kernel(const int *__restrict__ job_list, const int *__restrict
                 MgThreadFcn<N> fcn;
                 fcn.tile = smem_u32(tile + threadIdx.x); fcn.wtab = wtab; fcn.spl = cal.spline + (size_t)bn * (T - 1) * 4;
                 fcn.lsb = lsb; fcn.ncalls = 0; fcn.wlow = wlow; fcn.w0 = __ldg(wtab);
+                fcn.cap = 60 + 150 * N; fcn.aborted = false;     // ~3x the usual 64 / 123 / 192 evaluations of a first attempt
                 const double tref = cal.timeref[bn];
                 double *wt = wftime + (size_t)item * MAXP, *wa = wfampl + (size_t)item * MAXP;
                 mg::fit_seeds(sig, tref, wt, wa, N, start);
-                const mg::FitOutcome out = mg::fitwf_minimise<P>(fcn, W, N, start, werr);
+                // first attempt only (Migrad strategy 1, T2:755): a fit that fails it, or runs long, leaves for the warp kernel
+#pragma unroll
+                for (int i = 0; i < P; i++) werr[i] = (start[i] == 0) ? 0.3 : 0.3 * fabs(start[i]);
+                const mg::Result r1 = mg::migrad<P>(fcn, W, P, start, werr, 1, 1000u + 100u * P + 5u * P * P, 0.01);
+                if (fcn.aborted || !r1.valid) {
+                    ho_list[atomicAdd(ho_count, 1)] = raw;
+                    continue_next = true;
+                }
+                const mg::FitOutcome out{NPSWF_ST_FIT_OK1, r1.fval, r1.ncalls};
+                if (!continue_next) {
                 // write-back (T2:774-827)
                 const double corr = corr_time_HMS ? corr_time_HMS[e] : 0.0;
                 const double cort = (double)cal.cortime[bn];
@@ -446,6 +465,7 @@ fit_migrad_thread_kernel(const int *__restrict__ job_list, const int *__restrict
                 else c_fb++;
                 c_calls += (unsigned long long)out.ncalls;
                 c_att++;
+                }
             }
         }
         __syncwarp();

@@ -48,7 +48,9 @@ __device__ __forceinline__ float inv_err_f32(double v)
 // chi2 and normal equations of one fit at parameters p, all 90 points, one thread.
 // kn points at knot 0 of the block's zero-padded knot array.  U points per loop body; the loads of the next
 // body are issued before the arithmetic of the current one.
-template <int N, int U>
+// DIAG: only the diagonal of the normal matrix is accumulated (the variable-metric kernel needs chi2, its gradient and
+// its second derivatives along the axes, not the full Gauss-Newton matrix).
+template <int N, int U, bool DIAG = false>
 __device__ __forceinline__ void eval_thread(const double (&p)[2 * N + 1], const float2 *__restrict__ ywcol,
                                             const double2 *__restrict__ kn, NormalEq<2 * N + 1> &ne)
 {
@@ -131,7 +133,8 @@ __device__ __forceinline__ void eval_thread(const double (&p)[2 * N + 1], const 
             for (int a = 0; a < P; a++) {
                 ne.g[a] = fma(J[a], r, ne.g[a]);
 #pragma unroll
-                for (int b = 0; b <= a; b++) ne.H[a * (a + 1) / 2 + b] = fma(J[a], J[b], ne.H[a * (a + 1) / 2 + b]);
+                for (int b = 0; b <= a; b++)
+                    if (!DIAG || b == a) ne.H[a * (a + 1) / 2 + b] = fma(J[a], J[b], ne.H[a * (a + 1) / 2 + b]);
             }
         }
     };
@@ -156,6 +159,7 @@ __device__ __forceinline__ void eval_thread(const double (&p)[2 * N + 1], const 
         if (ta) ne.g[a] *= nA[(a - 1) >> 1];
 #pragma unroll
         for (int b = 0; b <= a; b++) {
+            if (DIAG && b != a) continue;
             const bool tb = b >= 1 && ((b - 1) & 1) == 0;
             if (ta && tb) ne.H[a * (a + 1) / 2 + b] *= nA[(a - 1) >> 1] * nA[(b - 1) >> 1];
             else if (ta) ne.H[a * (a + 1) / 2 + b] *= nA[(a - 1) >> 1];

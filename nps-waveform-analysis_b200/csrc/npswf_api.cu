@@ -20,6 +20,7 @@
 #include "kernel_fit.cuh"
 #include "kernel_fit_small.cuh"
 #include "kernel_fit_thread.cuh"
+#include "kernel_fit_vm.cuh"
 #include "kernel_aux.cuh"
 #include "migrad_launch.hpp"
 #include "host_pack.hpp"
@@ -49,7 +50,7 @@ struct Workspace {  // per (device, pipeline stage) buffers for up to `cap` even
     double *wftime = nullptr, *wfampl = nullptr, *chi2 = nullptr, *timewf = nullptr, *amplwf = nullptr;
     uint8_t *status = nullptr;
     uint8_t *mask = nullptr;
-    int *fit_count = nullptr;     // [64]: jobs per multiplicity, [16 + N]: job cursors, [32 + N]: continuation counts, [48 + N]: their cursors
+    int *fit_count = nullptr;     // [128]: jobs per multiplicity, [16 + N]: job cursors, [32 + N]: continuation counts, [48 + N]: their cursors, [64 + N] / [80 + N]: second-level hand-over counts / cursors
     int *cont_list = nullptr;     // [3][cap*B] fits handed from fit_thread_kernel to fit_small_kernel (N = 1, 2, 3)
     double *cont_state = nullptr; // [3][cap*B][10] their LM state
     int *bucket_count = nullptr;  // [13][B] jobs per (multiplicity, block)
@@ -80,6 +81,7 @@ struct DevSlot {
     bool fit_thread = true;     // thread-per-fit kernels for N = 1, 2 (env NPSWF_FIT_THREAD=0 selects the sub-warp kernels)
     int occ_fit_thread[5] = {0, 2, 2, 2, 2};   // [4]: N = 4..6
     int fit_thread_maxocc = 0;  // env NPSWF_FIT_THREAD_OCC: cap on resident CTAs per SM (fewer CTAs leave more L1)
+    int occ_vm_thread[4] = {0, 2, 2, 2};   // fit_vm_thread_kernel<1, 2, 3>
     int occ_migrad[3] = {2, 1, 1};   // fit_migrad_kernel<7, 13, 25>
     int occ_migrad_thread[4] = {0, 4, 4, 4};   // fit_migrad_thread_kernel<1, 2, 3>
     double *mg_wtab = nullptr;       // inverse error by |ADC count| (thread-per-fit Migrad kernels)
@@ -342,7 +344,7 @@ int alloc_workspace(npswf_handle *h, DevSlot &s, Workspace &w, int64_t cap, bool
         if ((rc = dev_alloc(h, s, &w.mask, nb))) return rc;
     }
     if ((rc = alloc_scratch(h, s, w, cap))) return rc;
-    if ((rc = dev_alloc(h, s, &w.fit_count, 64))) return rc;
+    if ((rc = dev_alloc(h, s, &w.fit_count, 128))) return rc;
     if ((rc = dev_alloc(h, s, &w.bucket_count, (size_t)(MAXP + 1) * B))) return rc;
     CU_TRY(h, cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
     CU_TRY(h, cudaEventCreateWithFlags(&w.ev_in, cudaEventDisableTiming));
@@ -484,8 +486,10 @@ int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, cons
         const int *list = w.fit_dense + (size_t)N * stride;
         const int *cnt = w.fit_count + N;
         int *next = w.fit_count + 16 + N;  // per-multiplicity job cursor, zeroed with fit_count
-        if (h->fit_mode == NPSWF_FIT_MIGRAD) {
+        const bool vm_fast = h->fit_mode == NPSWF_FIT_VM && N <= 3 && h->unit_knots && s.occ_vm_thread[N] > 0;
+        if (h->fit_mode == NPSWF_FIT_MIGRAD || (h->fit_mode == NPSWF_FIT_VM && !vm_fast)) {
             // the reference's own minimiser (Migrad, numerical gradients, strategy 1 -> 2), one warp per fit
+            // (VM mode: 4+ pulses and general knots have no analytic-path kernel and take the exact one)
             MigradArgs ma{list, cnt, next, N, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr};
             const int cls = migrad_class(N);
             if (N <= 3 && s.migrad_thread && s.occ_migrad_thread[N] > 0 && h->unit_knots) {
@@ -509,6 +513,27 @@ int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, cons
             } else {
                 CU_TRY(h, migrad_launch(cls, s.sm_count * s.occ_migrad[cls], st, ma));
             }
+        } else if (vm_fast) {
+            // Migrad's own recursion with analytic derivatives (kernel_fit_vm.cuh); what leaves the common path goes to
+            // the exact warp-per-fit Migrad kernel
+            int *ccnt = w.fit_count + 32 + N, *cnext = w.fit_count + 48 + N;
+            int *clist = w.cont_list + (size_t)(N - 1) * stride;
+            const int vgrid = s.sm_count * s.occ_vm_thread[N];
+            if (N == 1)
+                fit_vm_thread_kernel<1><<<vgrid, FT_THREADS, FT_SMEM, st>>>(list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2,
+                                                                            timewf, amplwf, status, s.ctr, ccnt, clist);
+            else if (N == 2)
+                fit_vm_thread_kernel<2><<<vgrid, FT_THREADS, FT_SMEM, st>>>(list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2,
+                                                                            timewf, amplwf, status, s.ctr, ccnt, clist);
+            else
+                fit_vm_thread_kernel<3><<<vgrid, FT_THREADS, FT_SMEM, st>>>(list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2,
+                                                                            timewf, amplwf, status, s.ctr, ccnt, clist);
+            CU_TRY(h, cudaGetLastError());
+            // the hand-over lists are short (~1 % of the fits): the warp-per-fit kernel finishes a fit in a fraction of a
+            // millisecond, a thread of the thread-per-fit kernel needs 3-50 ms for one, which would be the tail of the stage
+            MigradArgs ma{clist, ccnt, cnext, N, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr};
+            const int cls = migrad_class(N);
+            CU_TRY(h, migrad_launch(cls, s.sm_count * s.occ_migrad[cls], st, ma));
         } else if (!h->unit_knots) {
             // general interpX: the warp-per-fit LM kernel with a bisection per spline evaluation (both attempts)
             if (N <= 6)
@@ -591,7 +616,7 @@ int run_chunk(npswf_handle *h, DevSlot &s, Workspace &w, cudaStream_t st, int64_
               const int32_t *pres, const double *corr, int32_t *wfnpulse, double *wftime, double *wfampl, double *chi2,
               double *timewf, double *amplwf, uint8_t *status)
 {
-    CU_TRY(h, cudaMemsetAsync(w.fit_count, 0, 64 * sizeof(int), st));
+    CU_TRY(h, cudaMemsetAsync(w.fit_count, 0, 128 * sizeof(int), st));
     CU_TRY(h, cudaMemsetAsync(w.bucket_count, 0, (size_t)(MAXP + 1) * B * sizeof(int), st));
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     if (h->profiling) {
@@ -1051,8 +1076,11 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
     h->kp.fit_max_iter = cfg->fit_max_iter > 0 ? cfg->fit_max_iter : 60;
     h->kp.fit_retry_max_iter = cfg->fit_retry_max_iter > 0 ? cfg->fit_retry_max_iter : 100;
     h->kp.fit_thread_tries = (getenv("NPSWF_FIT_THREAD_TRIES") && atoi(getenv("NPSWF_FIT_THREAD_TRIES")) > 0) ? atoi(getenv("NPSWF_FIT_THREAD_TRIES")) : 20;
-    h->fit_mode = cfg->fit_mode == NPSWF_FIT_MIGRAD ? NPSWF_FIT_MIGRAD : NPSWF_FIT_FAST;
-    if (getenv("NPSWF_FIT_MODE")) h->fit_mode = atoi(getenv("NPSWF_FIT_MODE")) == 1 ? NPSWF_FIT_MIGRAD : NPSWF_FIT_FAST;   // A/B runs of unchanged callers
+    h->fit_mode = (cfg->fit_mode == NPSWF_FIT_MIGRAD || cfg->fit_mode == NPSWF_FIT_VM) ? cfg->fit_mode : NPSWF_FIT_FAST;
+    if (getenv("NPSWF_FIT_MODE")) {   // A/B runs of unchanged callers
+        const int m = atoi(getenv("NPSWF_FIT_MODE"));
+        h->fit_mode = (m == NPSWF_FIT_MIGRAD || m == NPSWF_FIT_VM) ? m : NPSWF_FIT_FAST;
+    }
     h->chunk = cfg->chunk_events > 0 ? cfg->chunk_events : 1184;
     h->chunk_fixed = cfg->chunk_events > 0;
     h->dev_cap = h->chunk_fixed ? h->chunk : 4736;
@@ -1264,6 +1292,12 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
         CR(cudaFuncSetAttribute(fit_thread_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
         CR(cudaFuncSetAttribute(fit_thread_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_thread[3], fit_thread_kernel<3>, FT_THREADS, FT_SMEM));
+        CR(cudaFuncSetAttribute(fit_vm_thread_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
+        CR(cudaFuncSetAttribute(fit_vm_thread_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
+        CR(cudaFuncSetAttribute(fit_vm_thread_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
+        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vm_thread[1], fit_vm_thread_kernel<1>, FT_THREADS, FT_SMEM));
+        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vm_thread[2], fit_vm_thread_kernel<2>, FT_THREADS, FT_SMEM));
+        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vm_thread[3], fit_vm_thread_kernel<3>, FT_THREADS, FT_SMEM));
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_thread[1], fit_thread_kernel<1>, FT_THREADS, FT_SMEM));
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_thread[2], fit_thread_kernel<2>, FT_THREADS, FT_SMEM));
         if (getenv("NPSWF_FIT_THREAD_OCC")) s.fit_thread_maxocc = atoi(getenv("NPSWF_FIT_THREAD_OCC"));
@@ -1796,7 +1830,7 @@ int npswf_fitwf_batch(npswf_handle *h, int64_t n_events, const double *signal, c
         CU_TRY(h, cudaMemcpyAsync(w.wfnpulse, wfnpulse + ob, nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         CU_TRY(h, cudaMemcpyAsync(w.wftime, wftime + ob * MAXP, nb * MAXP * sizeof(double), cudaMemcpyHostToDevice, st));
         CU_TRY(h, cudaMemcpyAsync(w.wfampl, wfampl + ob * MAXP, nb * MAXP * sizeof(double), cudaMemcpyHostToDevice, st));
-        CU_TRY(h, cudaMemsetAsync(w.fit_count, 0, 64 * sizeof(int), st));
+        CU_TRY(h, cudaMemsetAsync(w.fit_count, 0, 128 * sizeof(int), st));
         CU_TRY(h, cudaMemsetAsync(w.bucket_count, 0, (size_t)(MAXP + 1) * B * sizeof(int), st));
         build_jobs_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(w.mask, w.wfnpulse, (long long)nb, w.bucket_count,
                                                                        w.fit_list, (int)w.cap, w.chi2, w.status);
@@ -1918,6 +1952,23 @@ int npswf_debug_exact_ops(npswf_handle *h, int64_t n_trials, uint64_t seed, uint
     CU_TRY(h, cudaMemcpy(out, d, 16, cudaMemcpyDeviceToHost));
     mismatch[0] = out[0];
     mismatch[1] = out[1];
+    return 0;
+}
+
+int npswf_debug_vm_reasons(npswf_handle *h, uint64_t out[8], int reset)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (!out) return NPSWF_ERR_ARG;
+    CU_TRY(h, cudaSetDevice(h->slots[0].device));
+    CU_TRY(h, cudaDeviceSynchronize());
+    unsigned long long tmp[8];
+    CU_TRY(h, cudaMemcpyFromSymbol(tmp, g_vm_reason, sizeof tmp));
+    for (int i = 0; i < 8; i++) out[i] = tmp[i];
+    if (reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        CU_TRY(h, cudaMemcpyToSymbol(g_vm_reason, z, sizeof z));
+    }
     return 0;
 }
 

@@ -52,6 +52,8 @@ def main():
     h.sync_device(stream=st)
     t = h.stage_times()
     c = h.counters()
+    if os.environ.get("NPSWF_FIT_MODE") == "2":
+        print("vm hand-offs by reason [limit/inexact, g2<=0, edm<0, above edm, not descent]:", h.vm_reasons()[:5])
     import time
     h.set_profiling(False)
     torch.cuda.synchronize()
