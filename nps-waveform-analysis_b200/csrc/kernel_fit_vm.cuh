@@ -51,7 +51,7 @@ struct VmState {
 // one g2b_ (what the first cycle measures; the analytic value stands in for it), and stops once the step changes by
 // less than 30 % -- or, after cycle 0, when the gradient moved by less than 5 % (gprev -> gnew).  NegativeG2LineSearch
 // steps along an axis in units of this.
-__device__ __forceinline__ double vm_gstep(double x, double f, double gprev, double gnew, double g2a, double g2b_, double gs)
+__device__ __noinline__ double vm_gstep(double x, double f, double gprev, double gnew, double g2a, double g2b_, double gs)
 {
     constexpr double EPS = mg::EPS, EPS2 = mg::EPS2;
     const double dfmin = 8. * EPS2 * (fabs(f) + 1.0), vrysml = 8. * EPS * EPS;
@@ -98,6 +98,60 @@ __device__ __noinline__ void vm_posdef(double (&V)[P * (P + 1) / 2])
         for (int b = 0; b <= a; b++) V[a * (a + 1) / 2 + b] = A[a * P + b];
 }
 
+// NegativeG2LineSearch, the two pieces around its line search (rare: a second derivative <= 0 at the seeds; out of line
+// to keep the common path small -- the loop body of this kernel is an instruction-cache problem first).
+// Accept the best point along the axis and take the derivatives there:
+template <int P>
+__device__ __noinline__ void vm_ng_accept(VmState<P> &S)
+{
+    S.in_ng = false;
+    if (S.xvmin != 0.) {
+#pragma unroll 1
+        for (int a = 0; a < P; a++) {
+            S.x0[a] += S.xvmin * S.dir[a];
+            S.gs[a] = vm_gstep(S.x0[a], S.fvmin, S.g0[a], S.gb[a], S.g20[a], S.g2b[a], S.gs[a]);
+            S.g0[a] = S.gb[a];
+            S.g20[a] = S.g2b[a];
+        }
+        S.f0 = S.fvmin;
+    }
+}
+
+// ... and start the search along parameter ia, in units of the step Minuit's gradient calculator would hold for it
+template <int P>
+__device__ __noinline__ void vm_ng_begin(VmState<P> &S, int ia)
+{
+    constexpr double EPS = mg::EPS, EPS2 = mg::EPS2;
+    if (S.ng_iter == 0) {
+        // InitialGradientCalculator from the parameter step 0.3 |x| (0.3 for x = 0), then the seed's gradient cycles
+#pragma unroll 1
+        for (int a = 0; a < P; a++) {
+            const double gsmin = 8. * EPS2 * (fabs(S.x0[a]) + EPS2);
+            const double dirin = fmax(S.x0[a] == 0 ? 0.3 : 0.3 * fabs(S.x0[a]), gsmin);
+            const double g2i = 2.0 / (dirin * dirin);
+            S.gs[a] = vm_gstep(S.x0[a], S.f0, g2i * dirin, S.g0[a], g2i, S.g20[a], fmax(gsmin, 0.1 * dirin));
+        }
+    }
+    S.ng_iter++;
+    double gdel = 0, slamin = 0;
+#pragma unroll 1
+    for (int a = 0; a < P; a++) {
+        S.dir[a] = 0.0;
+        if (a == ia) {
+            S.dir[a] = (S.g0[a] < 0) ? S.gs[a] : -S.gs[a];
+            gdel = S.dir[a] * S.g0[a];
+            if (S.dir[a] != 0) slamin = fabs(S.x0[a] / S.dir[a]);
+        }
+    }
+    S.gdel = gdel;
+    if (fabs(slamin) < EPS) slamin = EPS;
+    S.slamin = slamin * EPS2;
+    S.overal = 1000.; S.undral = -100.;
+    S.slam = 1.0;
+    S.in_ng = true;
+    S.phase = VM_LS_A;
+}
+
 // Next step of the minimisation after the evaluation in flight returned (f, g, g2) at x0 + slam * dir (at the seeds
 // when fresh).  Mirrors VariableMetricBuilder / MnLineSearch / DavidonErrorUpdator as migrad_core.hpp states them.
 template <int P>
@@ -122,11 +176,6 @@ __device__ __forceinline__ int vm_advance(VmState<P> &S, double f, const double 
         for (int a = 0; a < P; a++) {
             S.g0[a] = g[a];
             S.g20[a] = g2[a];
-            // InitialGradientCalculator from the parameter step 0.3 |x| (0.3 for x = 0), then the seed's gradient cycles
-            const double gsmin = 8. * EPS2 * (fabs(S.x0[a]) + EPS2);
-            const double dirin = fmax(S.x0[a] == 0 ? 0.3 : 0.3 * fabs(S.x0[a]), gsmin);
-            const double g2i = 2.0 / (dirin * dirin);
-            S.gs[a] = vm_gstep(S.x0[a], f, g2i * dirin, g[a], g2i, g2[a], fmax(gsmin, 0.1 * dirin));
         }
         go = 5;
     } else if (S.phase == VM_LS_A) {
@@ -236,18 +285,7 @@ __device__ __forceinline__ int vm_advance(VmState<P> &S, double f, const double 
     double edm_s = 0;   // EDM x (1 + 3 dcovar), what the loop condition of VariableMetricBuilder looks at
     bool stop = false;
     if (ls_done && S.in_ng) {
-        // NegativeG2LineSearch: accept the best point along the axis, take the derivatives there, look again
-        S.in_ng = false;
-        if (S.xvmin != 0.) {
-#pragma unroll
-            for (int a = 0; a < P; a++) {
-                S.x0[a] += S.xvmin * S.dir[a];
-                S.gs[a] = vm_gstep(S.x0[a], S.fvmin, S.g0[a], S.gb[a], S.g20[a], S.g2b[a], S.gs[a]);
-                S.g0[a] = S.gb[a];
-                S.g20[a] = S.g2b[a];
-            }
-            S.f0 = S.fvmin;
-        }
+        vm_ng_accept<P>(S);
         ls_done = false;
         go = 5;
     }
@@ -268,24 +306,7 @@ __device__ __forceinline__ int vm_advance(VmState<P> &S, double f, const double 
             if (!(S.edm >= 0.)) { VM_REASON(1); return VM_HANDOFF; }   // still not positive: Migrad's seed is invalid, strategy 2 follows
             go = 1;
         } else {
-            S.ng_iter++;
-            double gdel = 0, slamin = 0;
-#pragma unroll
-            for (int a = 0; a < P; a++) {
-                S.dir[a] = 0.0;
-                if (a == ia) {
-                    S.dir[a] = (S.g0[a] < 0) ? S.gs[a] : -S.gs[a];
-                    gdel = S.dir[a] * S.g0[a];
-                    if (S.dir[a] != 0) slamin = fabs(S.x0[a] / S.dir[a]);
-                }
-            }
-            S.gdel = gdel;
-            if (fabs(slamin) < EPS) slamin = EPS;
-            S.slamin = slamin * EPS2;
-            S.overal = 1000.; S.undral = -100.;
-            S.slam = 1.0;
-            S.in_ng = true;
-            S.phase = VM_LS_A;
+            vm_ng_begin<P>(S, ia);
             return VM_EVAL;
         }
     }
@@ -397,8 +418,130 @@ __device__ __forceinline__ int vm_advance(VmState<P> &S, double f, const double 
     return VM_EVAL;
 }
 
+constexpr int VM_TILE_BYTES = (NFIT * FT_LD * (int)sizeof(float) + 15) / 16 * 16;   // the samples only: the weight is a function of the sample
+constexpr int VM_WARP_BYTES = VM_TILE_BYTES + 20 * (int)sizeof(double);   // + the 20 pedestal samples of the trace being loaded
+#ifndef NPSWF_VM_WARPS
+#define NPSWF_VM_WARPS 4
+#endif
+#ifndef NPSWF_VM_MINBLOCKS
+#define NPSWF_VM_MINBLOCKS 3
+#endif
+constexpr int VM_THREADS = NPSWF_VM_WARPS * 32;
+constexpr size_t VM_SMEM = (size_t)NPSWF_VM_WARPS * VM_WARP_BYTES;   // 11 880 B per warp -> registers, not shared memory, set the residency
+#ifndef NPSWF_VM_LOCKSTEP
+#define NPSWF_VM_LOCKSTEP 1
+#endif
+
+// chi2, d chi2 / d p_a and d2 chi2 / d p_a^2 of one fit at parameters p, all 90 points, one thread (the arithmetic of
+// eval_thread, kernel_fit_thread.cuh, without the off-diagonal normal matrix).  The tile holds the samples as binary32
+// (exact: other traces do not come here); the weight 1 / Err (T2:946-956) is recomputed per point on the FP32 / MUFU
+// pipes, which this kernel leaves idle -- bit for bit what inv_err_f32 stores for the Levenberg-Marquardt kernel.
+template <int N, int U>
+__device__ __forceinline__ void eval_vm(const double (&p)[2 * N + 1], const float *__restrict__ ycol, const double2 *__restrict__ kn,
+                                        double &c2_out, double (&g_out)[2 * N + 1], double (&g2_out)[2 * N + 1])
+{
+    constexpr int P = 2 * N + 1;
+    static_assert(NFIT % (2 * U) == 0, "2 U must divide the number of fit points");
+    const double2 *kp[N];
+    double2 k0[N];
+    double wa[N], wb[N], wc[N], wd[N], dc[N], dd[N], e0[N], e1[N], nA[N];
+    int jlo[N];
+    unsigned span[N];
+#pragma unroll
+    for (int n = 0; n < N; n++) {
+        double u = (double)MFSTART - p[1 + 2 * n];
+        u = fmin(fmax(u, -120.0), 120.0);   // a wild trial step stays inside the zero padding of the knot array
+        const double fl = floor(u);
+        const int i0 = (int)fl;
+        const double f = u - fl, g = 1.0 - f;
+        wa[n] = g; wb[n] = f;
+        wc[n] = (g * g * g - g) * (1.0 / 3.0); wd[n] = (f * f * f - f) * (1.0 / 3.0);
+        dc[n] = (1.0 - 3.0 * g * g) * (1.0 / 3.0); dd[n] = (3.0 * f * f - 1.0) * (1.0 / 3.0);
+        e0[n] = 2.0 * g; e1[n] = 2.0 * f;
+        nA[n] = -p[2 + 2 * n];
+        int jl = (int)floor(1.0 - u) + 1, jh = (int)ceil((double)(T - 1) - u) - 1;   // 1 < u + j < 109  (T2:629)
+        jl = max(jl, 0);
+        jh = min(jh, NFIT - 1);
+        if (jh < jl) { jl = 1 << 20; jh = jl; }
+        jlo[n] = jl; span[n] = (unsigned)(jh - jl);
+        kp[n] = kn + i0;
+        k0[n] = __ldg(kp[n]);
+    }
+    double c2 = 0, gs[P], hs[P], s2[N];
+#pragma unroll
+    for (int i = 0; i < P; i++) { gs[i] = 0; hs[i] = 0; }
+#pragma unroll
+    for (int n = 0; n < N; n++) s2[n] = 0;
+    const double p0 = p[0];
+    float yA[U], yB[U];
+    double2 kA[N][U], kB[N][U];
+    auto load = [&](int jb, float (&yy)[U], double2 (&kk)[N][U]) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            yy[u] = ycol[(jb + u) * FT_LD];
+#pragma unroll
+            for (int n = 0; n < N; n++) kk[n][u] = __ldg(kp[n] + jb + u + 1);
+        }
+    };
+    auto consume = [&](int jb, const float (&yy)[U], const double2 (&kk)[N][U]) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int j = jb + u;
+            const float af = fabsf(yy[u]);
+            float rs;
+            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(af));
+            const float wf = (af < 0x1.0624dep+3f) ? 0x1.6e5b7ep+1f : rs * 0x1.6e5b7ep+1f;   // = inv_err_f32((double)y)
+            const double wk = (double)wf;
+            double r = ((double)yy[u] - p0) * wk;
+            double J[P], d2w[N];
+            J[0] = wk;
+#pragma unroll
+            for (int n = 0; n < N; n++) {
+                const double2 k1 = kk[n][u];
+                const double wkm = ((unsigned)(j - jlo[n]) <= span[n]) ? wk : 0.0;
+                const double sp = fma(wd[n], k1.y, fma(wc[n], k0[n].y, fma(wb[n], k1.x, wa[n] * k0[n].x)));
+                const double ds = fma(dd[n], k1.y, fma(dc[n], k0[n].y, k1.x - k0[n].x));
+                const double d2 = fma(e1[n], k1.y, e0[n] * k0[n].y);
+                k0[n] = k1;
+                d2w[n] = d2 * wkm;
+                J[2 + 2 * n] = sp * wkm;
+                J[1 + 2 * n] = ds * wkm;   // without its factor -A_n: applied once to the sums after the loop
+                r = fma(nA[n], J[2 + 2 * n], r);
+            }
+            c2 = fma(r, r, c2);
+#pragma unroll
+            for (int n = 0; n < N; n++) s2[n] = fma(r, d2w[n], s2[n]);
+#pragma unroll
+            for (int a = 0; a < P; a++) {
+                gs[a] = fma(J[a], r, gs[a]);
+                hs[a] = fma(J[a], J[a], hs[a]);
+            }
+        }
+    };
+    load(0, yA, kA);
+#pragma unroll 1
+    for (int j0 = 0; j0 < NFIT; j0 += 2 * U) {
+        load(j0 + U, yB, kB);
+        consume(j0, yA, kA);
+        if (j0 + 2 * U < NFIT) load(j0 + 2 * U, yA, kA);
+        consume(j0 + U, yB, kB);
+    }
+    // d chi2 / d p_a = -2 sum r w df/dp_a;  d2 chi2 / d p_a^2 = 2 sum (w df/dp_a)^2 - 2 sum r w d2f/dp_a^2: the second term
+    // is zero for the parameters the model is linear in; the time columns get their factor(s) -A_n here
+    c2_out = c2;
+    g_out[0] = -2.0 * gs[0];
+    g2_out[0] = 2.0 * hs[0];
+#pragma unroll
+    for (int n = 0; n < N; n++) {
+        g_out[1 + 2 * n] = -2.0 * gs[1 + 2 * n] * nA[n];
+        g2_out[1 + 2 * n] = 2.0 * hs[1 + 2 * n] * (nA[n] * nA[n]) + 2.0 * (s2[n] * nA[n]);
+        g_out[2 + 2 * n] = -2.0 * gs[2 + 2 * n];
+        g2_out[2 + 2 * n] = 2.0 * hs[2 + 2 * n];
+    }
+}
+
 template <int N>
-__global__ void __launch_bounds__(FT_THREADS, 2)
+__global__ void __launch_bounds__(VM_THREADS, NPSWF_VM_MINBLOCKS)
 fit_vm_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_count, int *__restrict__ job_next,
                   const double *__restrict__ signal, const double *__restrict__ corr_time_HMS, DevCalib cal, KParams kp,
                   double *__restrict__ wftime, double *__restrict__ wfampl, double *__restrict__ chi2_out,
@@ -406,13 +549,18 @@ fit_vm_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ j
                   DeviceCounters *__restrict__ ctr, int *__restrict__ cont_count, int *__restrict__ cont_list)
 {
     constexpr int P = 2 * N + 1;
-    constexpr int U = (N == 1) ? 5 : 1;
-    constexpr double REL_TOL = FIT_REL_TOL;
+#ifndef NPSWF_VM_U1   // points per loop body of the evaluation: 1 measures best (code size before instruction-level parallelism)
+#define NPSWF_VM_U1 1
+#define NPSWF_VM_U2 1
+#define NPSWF_VM_U3 1
+#endif
+    constexpr int U = (N == 1) ? NPSWF_VM_U1 : (N == 2) ? NPSWF_VM_U2 : NPSWF_VM_U3;
     const unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char ft_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float2 *ywwarp = reinterpret_cast<float2 *>(ft_smem + (size_t)warp * FT_WARP_BYTES);   // [90][33] (sample, 1/err)
-    const float2 *ywcol = ywwarp + lane;
+    float *ywarp = reinterpret_cast<float *>(ft_smem + (size_t)warp * VM_WARP_BYTES);   // [90][33] samples
+    const float *ycol = ywarp + lane;
+    double *pedbuf = reinterpret_cast<double *>(ft_smem + (size_t)warp * VM_WARP_BYTES + VM_TILE_BYTES);
     const int njobs = *job_count;
     unsigned long long c_ok1 = 0, c_it = 0, c_att = 0, c_ev = 0;
 
@@ -430,76 +578,86 @@ fit_vm_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ j
     bool drained = false;   // the cursor has passed the end of the list
 
     for (;;) {
-        // ---- hand new jobs to the lanes without one (up to 4 traces in flight per round)
-        // (a round costs a few hundred issue slots whatever the number of idle lanes, so it waits for four of them
-        // unless the warp has nothing else to do)
+        // ---- hand new jobs to the lanes without one: one trace per turn of the loop, the next one's loads in flight
+        // meanwhile (a round costs a few hundred issue slots whatever the number of idle lanes, so it waits for four
+        // of them unless the warp has nothing else to do; ONE copy of the code: the loop body of the kernel has to
+        // stay small, see the note on lockstep below)
         unsigned m = __ballot_sync(FULL, !has_job && !exhausted);
         if (__popc(m) < 4 && __any_sync(FULL, has_job)) m = 0;
         bool got = false, inexact = false;
         double ped = 0;
-        while (m) {
-            int ls[4];
-            long long its[4];
-            double v[4][4];
+        int l_cur = -1, l_nxt = -1;
+        long long it_cur = -1, it_nxt = -1;
+        double v_cur[4], v_nxt[4];
+        // claim the next idle lane and the next job (warp-uniform), start the loads of its trace
+        auto claim = [&](int &l_out, long long &it_out, double (&v)[4]) {
+            l_out = -1; it_out = -1;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                ls[k] = -1; its[k] = -1;
+            for (int c4 = 0; c4 < 4; c4++) v[c4] = 0;
+            if (!m) return;
+            if (qpos == 32 && !drained) {   // claim the next 32 job ids, start pulling their traces into L2
+                int base = 0;
+                if (lane == 0) base = atomicAdd(job_next, 32);
+                base = __shfl_sync(FULL, base, 0);
+                const int j = base + lane;
+                q_item = (j < njobs) ? job_list[j] : -1;
+                qpos = 0;
+                drained = base + 32 >= njobs;
+                if (q_item >= 0) {
+                    const char *pt = reinterpret_cast<const char *>(signal + (size_t)q_item * T);
 #pragma unroll
-                for (int c4 = 0; c4 < 4; c4++) v[k][c4] = 0;
-                if (m) {
-                    if (qpos == 32 && !drained) {   // claim the next 32 job ids, start pulling their traces into L2
-                        int base = 0;
-                        if (lane == 0) base = atomicAdd(job_next, 32);
-                        base = __shfl_sync(FULL, base, 0);
-                        const int j = base + lane;
-                        q_item = (j < njobs) ? job_list[j] : -1;
-                        qpos = 0;
-                        drained = base + 32 >= njobs;
-                        if (q_item >= 0) {
-                            const char *pt = reinterpret_cast<const char *>(signal + (size_t)q_item * T);
-#pragma unroll
-                            for (int c = 0; c < 7; c++) prefetch_l2(pt + 128 * c);
-                            prefetch_l2(pt + T * 8 - 8);
-                        }
-                    }
-                    const int l = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int it = (qpos < 32) ? __shfl_sync(FULL, q_item, qpos) : -1;
-                    if (qpos < 32) qpos++;
-                    ls[k] = l;
-                    its[k] = it;
-                    if (it >= 0) {
-                        const double *src = signal + (size_t)it * T;
-#pragma unroll
-                        for (int c4 = 0; c4 < 4; c4++) {
-                            const int c = 32 * c4 + lane;
-                            if (c < T) v[k][c4] = src[c];
-                        }
-                    }
+                    for (int c = 0; c < 7; c++) prefetch_l2(pt + 128 * c);
+                    prefetch_l2(pt + T * 8 - 8);
                 }
             }
+            l_out = __ffs(m) - 1;
+            m &= m - 1;
+            const int it = (qpos < 32) ? __shfl_sync(FULL, q_item, qpos) : -1;
+            if (qpos < 32) qpos++;
+            it_out = it;
+            if (it >= 0) {
+                const double *src = signal + (size_t)it * T;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (ls[k] >= 0) {   // warp-uniform
-                    // pedestal seed = mean of the first 20 samples (T2:671-677); a seed: its last bit does not matter
-                    const double sum = warp_sum(lane < 20 ? v[k][0] : 0.0);
-                    bool exact = true;
-#pragma unroll
-                    for (int c4 = 0; c4 < 4; c4++) {
-                        const int c = 32 * c4 + lane;
-                        if (c >= MFSTART && c < MFEND && its[k] >= 0) {
-                            const float yf = (float)v[k][c4];
-                            exact = exact && ((double)yf == v[k][c4]) && (fabsf(yf) <= 3.0e38f);   // NaN fails the first test, +-Inf the second
-                            ywwarp[(c - MFSTART) * FT_LD + ls[k]] = make_float2(yf, inv_err_f32(v[k][c4]));
-                        }
-                    }
-                    exact = __all_sync(FULL, exact);
-                    if (lane == ls[k]) {
-                        if (its[k] >= 0) { item = its[k]; ped = sum / 20; got = true; inexact = !exact; }
-                        else exhausted = true;
-                    }
+                for (int c4 = 0; c4 < 4; c4++) {
+                    const int c = 32 * c4 + lane;
+                    if (c < T) v[c4] = src[c];
                 }
             }
+        };
+        claim(l_cur, it_cur, v_cur);
+#pragma unroll 1
+        while (l_cur >= 0) {   // warp-uniform
+            claim(l_nxt, it_nxt, v_nxt);
+            // pedestal seed = mean of the first 20 samples (T2:671-677), summed in the reference's order (through shared
+            // memory: a shuffle tree inside this loop compiles to five guarded copies of every shuffle)
+            __syncwarp();
+            if (lane < 20) pedbuf[lane] = v_cur[0];
+            __syncwarp();
+            double sum = 0;
+#pragma unroll
+            for (int i = 0; i < 20; i += 2) {
+                const double2 pv = *reinterpret_cast<const double2 *>(pedbuf + i);
+                sum += pv.x;
+                sum += pv.y;
+            }
+            bool exact = true;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; c4++) {
+                const int c = 32 * c4 + lane;
+                if (c >= MFSTART && c < MFEND && it_cur >= 0) {
+                    const float yf = (float)v_cur[c4];
+                    exact = exact && ((double)yf == v_cur[c4]) && (fabsf(yf) <= 3.0e38f);   // NaN fails the first test, +-Inf the second
+                    ywarp[(c - MFSTART) * FT_LD + l_cur] = yf;
+                }
+            }
+            exact = __all_sync(FULL, exact);
+            if (lane == l_cur) {
+                if (it_cur >= 0) { item = it_cur; ped = sum / 20; got = true; inexact = !exact; }
+                else exhausted = true;
+            }
+            l_cur = l_nxt; it_cur = it_nxt;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; c4++) v_cur[c4] = v_nxt[c4];
         }
         __syncwarp();
         if (got) {
@@ -516,29 +674,25 @@ fit_vm_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ j
             S.phase = VM_FRESH; S.iters = 0; S.slam = 0;
             S.nev = inexact ? (1 << 20) : 0;   // samples not exact in binary32: the fit goes to the Migrad kernels, which take any doubles
         }
+#if NPSWF_VM_LOCKSTEP
+        // the warps of a CTA walk the loop body together: the body is larger than the instruction cache next to the SM,
+        // and warps that drift apart each stream it from L2 on their own
+        if (!__syncthreads_or(has_job)) break;
+#else
         if (!__any_sync(FULL, has_job)) break;
+#endif
 
         // ---- one chi2 evaluation (value, gradient, second derivatives along the axes) at the point the lane's
         // minimisation asks for: the seeds, or a point of the current line search
         double trial[P];
 #pragma unroll
         for (int i = 0; i < P; i++) trial[i] = S.x0[i] + (S.phase == VM_FRESH ? 0.0 : S.slam * S.dir[i]);
-        NormalEq<P> nxt;
-        eval_thread<N, U, true>(trial, ywcol, kn, nxt);
+        double fv, g[P], g2[P];
+        eval_vm<N, U>(trial, ycol, kn, fv, g, g2);
         bool finished = false, handoff = false;
         if (has_job) {
             c_ev++;
-            // d chi2 / d p_a = -2 sum r w df/dp_a = -2 g[a];  d2 chi2 / d p_a^2 = 2 (J^T J)_aa - 2 sum r w d2f/dp_a^2: the second
-            // term is s2 for a pulse time and zero for the parameters the model is linear in
-            double g[P], g2[P];
-#pragma unroll
-            for (int a = 0; a < P; a++) {
-                g[a] = -2.0 * nxt.g[a];
-                g2[a] = 2.0 * nxt.H[a * (a + 1) / 2 + a];
-            }
-#pragma unroll
-            for (int n = 0; n < N; n++) g2[1 + 2 * n] += 2.0 * nxt.s2[n];
-            const int act = vm_advance<P>(S, nxt.c2, g, g2);
+            const int act = vm_advance<P>(S, fv, g, g2);
             finished = act == VM_DONE;
             handoff = act == VM_HANDOFF;
         }

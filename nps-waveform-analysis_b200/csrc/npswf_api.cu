@@ -520,13 +520,13 @@ int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, cons
             int *clist = w.cont_list + (size_t)(N - 1) * stride;
             const int vgrid = s.sm_count * s.occ_vm_thread[N];
             if (N == 1)
-                fit_vm_thread_kernel<1><<<vgrid, FT_THREADS, FT_SMEM, st>>>(list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2,
+                fit_vm_thread_kernel<1><<<vgrid, VM_THREADS, VM_SMEM, st>>>(list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2,
                                                                             timewf, amplwf, status, s.ctr, ccnt, clist);
             else if (N == 2)
-                fit_vm_thread_kernel<2><<<vgrid, FT_THREADS, FT_SMEM, st>>>(list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2,
+                fit_vm_thread_kernel<2><<<vgrid, VM_THREADS, VM_SMEM, st>>>(list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2,
                                                                             timewf, amplwf, status, s.ctr, ccnt, clist);
             else
-                fit_vm_thread_kernel<3><<<vgrid, FT_THREADS, FT_SMEM, st>>>(list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2,
+                fit_vm_thread_kernel<3><<<vgrid, VM_THREADS, VM_SMEM, st>>>(list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2,
                                                                             timewf, amplwf, status, s.ctr, ccnt, clist);
             CU_TRY(h, cudaGetLastError());
             // the hand-over lists are short (~1 % of the fits): the warp-per-fit kernel finishes a fit in a fraction of a
@@ -1292,12 +1292,12 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
         CR(cudaFuncSetAttribute(fit_thread_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
         CR(cudaFuncSetAttribute(fit_thread_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_thread[3], fit_thread_kernel<3>, FT_THREADS, FT_SMEM));
-        CR(cudaFuncSetAttribute(fit_vm_thread_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
-        CR(cudaFuncSetAttribute(fit_vm_thread_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
-        CR(cudaFuncSetAttribute(fit_vm_thread_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
-        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vm_thread[1], fit_vm_thread_kernel<1>, FT_THREADS, FT_SMEM));
-        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vm_thread[2], fit_vm_thread_kernel<2>, FT_THREADS, FT_SMEM));
-        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vm_thread[3], fit_vm_thread_kernel<3>, FT_THREADS, FT_SMEM));
+        CR(cudaFuncSetAttribute(fit_vm_thread_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VM_SMEM));
+        CR(cudaFuncSetAttribute(fit_vm_thread_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VM_SMEM));
+        CR(cudaFuncSetAttribute(fit_vm_thread_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VM_SMEM));
+        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vm_thread[1], fit_vm_thread_kernel<1>, VM_THREADS, VM_SMEM));
+        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vm_thread[2], fit_vm_thread_kernel<2>, VM_THREADS, VM_SMEM));
+        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vm_thread[3], fit_vm_thread_kernel<3>, VM_THREADS, VM_SMEM));
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_thread[1], fit_thread_kernel<1>, FT_THREADS, FT_SMEM));
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_thread[2], fit_thread_kernel<2>, FT_THREADS, FT_SMEM));
         if (getenv("NPSWF_FIT_THREAD_OCC")) s.fit_thread_maxocc = atoi(getenv("NPSWF_FIT_THREAD_OCC"));
