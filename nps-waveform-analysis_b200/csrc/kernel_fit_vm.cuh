@@ -24,11 +24,15 @@
 #include "kernel_fit_thread.cuh"
 #include "migrad_core.hpp"
 
+
 namespace npswf {
 
 enum { VM_FRESH = 0, VM_LS_A = 1, VM_LS_B = 2, VM_LS_C = 3 };   // what the evaluation in flight is
 enum { VM_EVAL = 0, VM_DONE = 1, VM_HANDOFF = 2 };              // what vm_advance asks for next
-constexpr int VM_MAX_EVALS = 48;                                 // beyond this the exact kernels take the fit
+#ifndef NPSWF_VM_MAX_EVALS
+#define NPSWF_VM_MAX_EVALS 48
+#endif
+constexpr int VM_MAX_EVALS = NPSWF_VM_MAX_EVALS;                 // beyond this the exact kernels take the fit
 // why fits left the kernel (diagnostics; read by npswf_debug_vm_reasons): 0 evaluation limit / inexact trace, 1 second
 // derivative <= 0 at the seeds, 2 EDM negative or not a number, 3 above the EDM limit, 4 not a descent direction
 __device__ unsigned long long g_vm_reason[8];
@@ -68,6 +72,14 @@ __device__ __noinline__ double vm_gstep(double x, double f, double gprev, double
     if (fabs((step1 - step) / step1) < 0.3) return gs;
     return step1;
 }
+
+// One copy of the binary64 division sequence for the whole kernel (inlined, each of the ~20 quotients of the common path
+// costs ~20 instructions of a loop body that has to stay inside the instruction cache)
+#if NPSWF_VM_DIV_CALL
+__device__ __noinline__ double vm_div(double a, double b) { return a / b; }
+#else
+__device__ __forceinline__ double vm_div(double a, double b) { return a / b; }
+#endif
 
 template <int P>
 __device__ __forceinline__ double vm_edm(const double (&V)[P * (P + 1) / 2], const double (&g)[P])
@@ -238,8 +250,8 @@ __device__ __forceinline__ int vm_advance(VmState<P> &S, double f, const double 
 
     // ---- the straight-line pieces between evaluations
     if (go == 2) {   // first loop of MnLineSearch: the point where the parabola through f0, gdel and the last value has its minimum
-        double denom = 2. * (S.flast - S.f0 - S.gdel * S.slam) / (S.slam * S.slam);
-        if (denom != 0) S.slam = -S.gdel / denom;
+        double denom = vm_div(2. * (S.flast - S.f0 - S.gdel * S.slam), S.slam * S.slam);
+        if (denom != 0) S.slam = vm_div(-S.gdel, denom);
         else S.slam = 1.;
         if (S.slam < 0.) S.slam = S.slamax;
         if (S.slam > S.slamax) S.slam = S.slamax;
@@ -256,16 +268,19 @@ __device__ __forceinline__ int vm_advance(VmState<P> &S, double f, const double 
         S.slamax = fmax(S.slamax, alpha * fabs(S.xvmin));
         double x1 = S.p0x, x2 = S.p1x, x3 = S.p2x;
         const double dx12 = x1 - x2, dx13 = x1 - x3, dx23 = x2 - x3;
-        const double xm = (x1 + x2 + x3) / 3.;
+        const double xm = (x1 + x2 + x3) * (1.0 / 3.0);
         x1 -= xm; x2 -= xm; x3 -= xm;
-        const double pa = S.p0y / (dx12 * dx13) - S.p1y / (dx12 * dx23) + S.p2y / (dx13 * dx23);
-        double pb = -S.p0y * (x2 + x3) / (dx12 * dx13) + S.p1y * (x1 + x3) / (dx12 * dx23) - S.p2y * (x1 + x2) / (dx13 * dx23);
+        // (three reciprocals instead of Minuit's six quotients: the last bit of lambda is far below what the analytic
+        // gradients already differ by)
+        const double q0 = vm_div(S.p0y, dx12 * dx13), q1 = vm_div(S.p1y, dx12 * dx23), q2 = vm_div(S.p2y, dx13 * dx23);
+        const double pa = q0 - q1 + q2;
+        double pb = -q0 * (x2 + x3) + q1 * (x1 + x3) - q2 * (x1 + x2);
         pb -= 2. * xm * pa;
         if (pa < EPS2) {
             const double slopem = 2. * pa * S.xvmin + pb;
             S.slam = (slopem < 0.) ? S.xvmin + S.slamax : S.xvmin - S.slamax;
         } else {
-            S.slam = -pb / (2. * pa);
+            S.slam = vm_div(-pb, 2. * pa);
             if (S.slam > S.xvmin + S.slamax) S.slam = S.xvmin + S.slamax;
             if (S.slam < S.xvmin - S.slamax) S.slam = S.xvmin - S.slamax;
         }
@@ -300,7 +315,7 @@ __device__ __forceinline__ int vm_advance(VmState<P> &S, double f, const double 
 #pragma unroll
             for (int i = 0; i < P * (P + 1) / 2; i++) S.V[i] = 0.0;
 #pragma unroll
-            for (int a = 0; a < P; a++) S.V[a * (a + 1) / 2 + a] = (fabs(S.g20[a]) > EPS2) ? 1.0 / S.g20[a] : 1.0;
+            for (int a = 0; a < P; a++) S.V[a * (a + 1) / 2 + a] = (fabs(S.g20[a]) > EPS2) ? vm_div(1.0, S.g20[a]) : 1.0;
             S.dcovar = 1.0;
             S.edm = vm_edm<P>(S.V, S.g0);
             if (!(S.edm >= 0.)) { VM_REASON(1); return VM_HANDOFF; }   // still not positive: Migrad's seed is invalid, strategy 2 follows
@@ -345,7 +360,7 @@ __device__ __forceinline__ int vm_advance(VmState<P> &S, double f, const double 
 #pragma unroll
             for (int a = 0; a < P; a++) gvg = fma(dg[a], vg[a], gvg);
             if (delgam != 0 && gvg > 0) {
-                const double rd = 1.0 / delgam, rg = 1.0 / gvg;
+                const double rd = vm_div(1.0, delgam), rg = vm_div(1.0, gvg);
                 const bool rank2 = delgam > gvg;
                 double sum_upd = 0, sum_v = 0;
 #pragma unroll
@@ -359,7 +374,7 @@ __device__ __forceinline__ int vm_advance(VmState<P> &S, double f, const double 
                         S.V[a * (a + 1) / 2 + b] = v;
                         sum_v += fabs(v);
                     }
-                S.dcovar = 0.5 * (S.dcovar + sum_upd / sum_v);
+                S.dcovar = 0.5 * (S.dcovar + vm_div(sum_upd, sum_v));
             }
 #pragma unroll
             for (int a = 0; a < P; a++) { S.x0[a] += dx[a]; S.g0[a] = gn[a]; }
@@ -406,7 +421,7 @@ __device__ __forceinline__ int vm_advance(VmState<P> &S, double f, const double 
 #pragma unroll
     for (int a = 0; a < P; a++) {
         if (S.dir[a] != 0) {
-            const double ratio = fabs(S.x0[a] / S.dir[a]);
+            const double ratio = fabs(vm_div(S.x0[a], S.dir[a]));
             if (slamin == 0 || ratio < slamin) slamin = ratio;
         }
     }
@@ -426,8 +441,14 @@ constexpr int VM_WARP_BYTES = VM_TILE_BYTES + 20 * (int)sizeof(double);   // + t
 #ifndef NPSWF_VM_MINBLOCKS
 #define NPSWF_VM_MINBLOCKS 3
 #endif
+#ifndef NPSWF_VM_MINBLOCKS1   // single-pulse instance: 114 registers as it stands; a fourth CTA measures the same
+#define NPSWF_VM_MINBLOCKS1 3
+#endif
 constexpr int VM_THREADS = NPSWF_VM_WARPS * 32;
 constexpr size_t VM_SMEM = (size_t)NPSWF_VM_WARPS * VM_WARP_BYTES;   // 11 880 B per warp -> registers, not shared memory, set the residency
+#ifndef NPSWF_VM_DIV_CALL
+#define NPSWF_VM_DIV_CALL 1
+#endif
 #ifndef NPSWF_VM_LOCKSTEP
 #define NPSWF_VM_LOCKSTEP 1
 #endif
@@ -541,7 +562,7 @@ __device__ __forceinline__ void eval_vm(const double (&p)[2 * N + 1], const floa
 }
 
 template <int N>
-__global__ void __launch_bounds__(VM_THREADS, NPSWF_VM_MINBLOCKS)
+__global__ void __launch_bounds__(VM_THREADS, (N == 1) ? NPSWF_VM_MINBLOCKS1 : NPSWF_VM_MINBLOCKS)
 fit_vm_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_count, int *__restrict__ job_next,
                   const double *__restrict__ signal, const double *__restrict__ corr_time_HMS, DevCalib cal, KParams kp,
                   double *__restrict__ wftime, double *__restrict__ wfampl, double *__restrict__ chi2_out,

@@ -18,7 +18,11 @@ METRICS = [
     "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
     "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
     "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static",
-]
+    "smsp__thread_inst_executed_per_inst_executed.ratio", "sass__inst_executed_local_loads", "sass__inst_executed_local_stores",
+    "l1tex__t_sector_pipe_lsu_mem_local_op_ld_hit_rate.pct",
+] + ["smsp__pcsamp_warps_issue_stalled_" + r for r in (
+    "barrier", "branch_resolving", "long_scoreboard", "short_scoreboard", "math_pipe_throttle", "no_instructions", "not_selected",
+    "selected", "wait", "dispatch_stall", "mio_throttle", "lg_throttle")]
 
 
 def main():
