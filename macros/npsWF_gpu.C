@@ -24,7 +24,8 @@ extern Float_t cortime[1080];
 extern Int_t preswf[1080];
 extern Double_t timerefacc;
 
-// tdcoffset: T2:368-375; timemean2: T2:526-529; fit_mode: NPSWF_FIT_MIGRAD reproduces Minuit2's path, NPSWF_FIT_FAST is ~10x faster
+// tdcoffset: T2:368-375; timemean2: T2:526-529; fit_mode: NPSWF_FIT_MIGRAD reproduces Minuit2's path bit for bit,
+// NPSWF_FIT_VM follows it with analytic derivatives (~4x faster), NPSWF_FIT_FAST (Levenberg-Marquardt) is ~8x faster
 void npsWF_gpu_event_loop(TTree *T, TTree *WF, const Float_t *tdcoffset, const Float_t *timemean2, int batch_events = 592,
                           int fit_mode = NPSWF_FIT_MIGRAD)
 {
