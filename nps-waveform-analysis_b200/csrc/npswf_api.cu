@@ -1960,14 +1960,17 @@ int npswf_debug_vm_reasons(npswf_handle *h, uint64_t out[8], int reset)
     int rc = check_handle(h);
     if (rc) return rc;
     if (!out) return NPSWF_ERR_ARG;
-    CU_TRY(h, cudaSetDevice(h->slots[0].device));
-    CU_TRY(h, cudaDeviceSynchronize());
-    unsigned long long tmp[8];
-    CU_TRY(h, cudaMemcpyFromSymbol(tmp, g_vm_reason, sizeof tmp));
-    for (int i = 0; i < 8; i++) out[i] = tmp[i];
-    if (reset) {
-        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        CU_TRY(h, cudaMemcpyToSymbol(g_vm_reason, z, sizeof z));
+    for (int i = 0; i < 8; i++) out[i] = 0;
+    for (size_t d = 0; d < h->slots.size(); d++) {   // the tallies live on each device the handle runs on
+        CU_TRY(h, cudaSetDevice(h->slots[d].device));
+        CU_TRY(h, cudaDeviceSynchronize());
+        unsigned long long tmp[8];
+        CU_TRY(h, cudaMemcpyFromSymbol(tmp, g_vm_reason, sizeof tmp));
+        for (int i = 0; i < 8; i++) out[i] += tmp[i];
+        if (reset) {
+            unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            CU_TRY(h, cudaMemcpyToSymbol(g_vm_reason, z, sizeof z));
+        }
     }
     return 0;
 }
