@@ -111,7 +111,7 @@ def main():
         print(json.dumps({
             "workload": "BASELINE configs[3]: %d synthetic events (config-%d content), generated on device per batch of %d, "
                         "contiguous event ranges per GPU" % (args.events, args.config, E),
-            "n_gpus": world, "fit_mode": "MIGRAD" if args.fit_mode == 1 else "FAST", "events": events, "fitted_block_waveforms": fitted,
+            "n_gpus": world, "fit_mode": {0: "FAST", 1: "MIGRAD", 2: "VM"}.get(args.fit_mode, str(args.fit_mode)), "events": events, "fitted_block_waveforms": fitted,
             "seconds": ms * 1e-3, "wall_seconds": wall, "fitted_block_waveforms_per_s": fitted / (ms * 1e-3),
             "events_per_s": events / (ms * 1e-3), "generator_share": gen_ms_per_batch * batches / ms,
             "fitted_block_waveforms_per_s_excluding_generation": fitted / ((ms - gen_ms_per_batch * batches) * 1e-3),
