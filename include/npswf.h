@@ -73,7 +73,7 @@ typedef struct NpsWfConfig {
  *   leave the common path go through the exact kernels): it follows Migrad into the same minimum and stops where
  *   Migrad stops on 99.99 % of ordinary fits (99.8 % with up to 12 pulses near threshold), at a quarter of MIGRAD's
  *   cost; 4+ pulses run through the exact kernels.
- * NPSWF_FIT_FAST: Levenberg-Marquardt on analytic spline derivatives (fit_thread_kernel & co.), ~10x cheaper; it
+ * NPSWF_FIT_FAST: Levenberg-Marquardt on analytic spline derivatives (fit_thread_kernel & co.), ~8x cheaper than MIGRAD; it
  *   converges the same chi2 tighter than Migrad's EDM goal, and where the chi2 has several local minima it may end
  *   in another one than Migrad does. */
 enum { NPSWF_FIT_FAST = 0, NPSWF_FIT_MIGRAD = 1, NPSWF_FIT_VM = 2 };
