@@ -53,7 +53,7 @@ def main():
     t = h.stage_times()
     c = h.counters()
     if os.environ.get("NPSWF_FIT_MODE") == "2":
-        print("vm hand-offs by reason [limit/inexact, g2<=0, edm<0, above edm, not descent]:", h.vm_reasons()[:5])
+        r = h.vm_reasons(); print("vm hand-offs by reason [limit/inexact, g2<=0, edm<0, above edm, not descent]:", r[:5], "| other tallies:", r[5:])
     import time
     h.set_profiling(False)
     torch.cuda.synchronize()
