@@ -69,10 +69,10 @@ typedef struct NpsWfConfig {
  *   (csrc/migrad_core.hpp, fit_migrad_kernel) in the reference's FMA-free arithmetic and summation order: fitted
  *   values, chi2 and the ok / retry / fall-back verdict follow Migrad's path.
  * NPSWF_FIT_VM: Migrad's recursion (seed from the second derivatives, MnLineSearch, Davidon update, EDM stop) with
- *   ANALYTIC gradients instead of Minuit's numerical ones and no MnHesse (fit_vm_thread_kernel, 1-3 pulses; fits that
- *   leave the common path go through the exact kernels): it follows Migrad into the same minimum and stops where
- *   Migrad stops on 99.99 % of ordinary fits (99.8 % with up to 12 pulses near threshold), at a quarter of MIGRAD's
- *   cost; 4+ pulses run through the exact kernels.
+ *   ANALYTIC gradients instead of Minuit's numerical ones and no MnHesse (fit_vm_thread_kernel, 1-6 pulses; fits that
+ *   leave the common path, 7+ pulses and general knots go through the exact kernels): it follows Migrad into the same
+ *   minimum and stops where Migrad stops on 99.99 % of ordinary fits (99.5 % with up to 12 pulses near threshold), at
+ *   a quarter of MIGRAD's cost.
  * NPSWF_FIT_FAST: Levenberg-Marquardt on analytic spline derivatives (fit_thread_kernel & co.), ~8x cheaper than MIGRAD; it
  *   converges the same chi2 tighter than Migrad's EDM goal, and where the chi2 has several local minima it may end
  *   in another one than Migrad does. */

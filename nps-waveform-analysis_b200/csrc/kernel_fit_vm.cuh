@@ -10,16 +10,21 @@
 // runs the same recursion -- seed, MnLineSearch, Davidon update, EDM stop (migrad_core.hpp spells them out for the
 // exact kernels) -- with analytic gradients and second derivatives from the pass that evaluates chi2 anyway, and no
 // MnHesse at the end (it does not move the parameters): ~11 evaluations per single-pulse fit instead of 65, and the
-// same minimum as the CPU oracle's Migrad on 99.98 % / 99.3 % of the fits (CPU experiment on the oracle).
+// same minimum as the CPU oracle's Migrad on 99.99 % (1-3 pulses) / 99.5 % (up to 12 near threshold) of the fits
+// (tests/test_gpu_migrad.py::test_vm_mode_follows_migrad).
 // It stops where Migrad stops (it does not converge further: the reference's numbers are Migrad's stopping points).
-// Anything off the common path -- a non-positive second derivative at the seeds (NegativeG2LineSearch), a direction
-// that is not a descent (MnPosDef), EDM above the limit, too many evaluations, a trace that is not exact in binary32 --
-// is handed, untouched, to the exact Migrad kernels (fit_migrad_*), which run it from its seeds with the reference's
-// retry / fall-back policy.
+// NegativeG2LineSearch (a non-positive second derivative at the seeds) and MnPosDef (a direction that is not a descent)
+// are followed in the kernel, out of line.  What leaves the common path for good -- EDM above the limit when the
+// iterations end, too many evaluations, an invalid seed state, a trace that is not exact in binary32 -- is handed,
+// untouched, to the exact Migrad kernels (fit_migrad_*), which run it from its seeds with the reference's retry /
+// fall-back policy.
 //
-// Same machinery as fit_thread_kernel (kernel_fit_thread.cuh): one thread per fit, the 90 samples and weights as
-// float2 in shared memory, persistent lanes fed from the warp's job queue, one chi2 pass per trip of the main loop;
-// the minimiser is a per-lane state machine around that single evaluation site.
+// Same machinery as fit_thread_kernel (kernel_fit_thread.cuh): one thread per fit (1-6 pulses), persistent lanes fed
+// from the warp's job queue, one chi2 pass per trip of the main loop, the minimiser a per-lane state machine around
+// that single evaluation site.  Its own: the tile holds the samples only (binary32; the weight is recomputed per
+// point), the evaluation accumulates chi2, gradient and the diagonal second derivatives only, and everything is
+// written for a SMALL loop body -- the kernel was bound by instruction fetches before it was bound by anything else
+// (rare branches out of line, a single-copy trace loader, one point per loop body, the warps of a CTA in lockstep).
 #pragma once
 #include "kernel_fit_thread.cuh"
 #include "migrad_core.hpp"
@@ -32,7 +37,10 @@ enum { VM_EVAL = 0, VM_DONE = 1, VM_HANDOFF = 2 };              // what vm_advan
 #ifndef NPSWF_VM_MAX_EVALS
 #define NPSWF_VM_MAX_EVALS 48
 #endif
-constexpr int VM_MAX_EVALS = NPSWF_VM_MAX_EVALS;                 // beyond this the exact kernels take the fit
+// beyond this many evaluations the exact kernels take the fit: 48 for 1-3 pulses (100 / 250 would save 2-4 % of the
+// stage for 0.07-0.1 point of agreement); 96 / 128 / 160 for 4 / 5 / 6 pulses, whose fits need more iterations and whose
+// hand-overs run one warp per fit for milliseconds each
+__host__ __device__ constexpr int vm_max_evals(int P) { return P <= 7 ? NPSWF_VM_MAX_EVALS : 16 * (P - 3); }
 // why fits left the kernel (diagnostics; read by npswf_debug_vm_reasons): 0 evaluation limit / inexact trace, 1 second
 // derivative <= 0 at the seeds, 2 EDM negative or not a number, 3 above the EDM limit, 4 not a descent direction
 __device__ unsigned long long g_vm_reason[8];
@@ -173,7 +181,7 @@ __device__ __forceinline__ int vm_advance(VmState<P> &S, double f, const double 
     constexpr double toler = 0.05, slambg = 5., alpha = 2., edmval = 0.002 * 0.01;
     constexpr int maxiter = 12;
     S.nev++;
-    if (S.nev > VM_MAX_EVALS) { VM_REASON(0); return VM_HANDOFF; }
+    if (S.nev > vm_max_evals(P)) { VM_REASON(0); return VM_HANDOFF; }
     bool ls_done = false;
     int go = 0;   // 1: begin an iteration, 2: first loop of the line search, 3: its second loop, 4: its inner check
 
@@ -441,6 +449,12 @@ constexpr int VM_WARP_BYTES = VM_TILE_BYTES + 20 * (int)sizeof(double);   // + t
 #ifndef NPSWF_VM_MINBLOCKS
 #define NPSWF_VM_MINBLOCKS 3
 #endif
+#ifndef NPSWF_VM_MINBLOCKS4   // 4-6 pulses: 9-13 parameters, the evaluation's sums alone are 40-56 registers
+#define NPSWF_VM_MINBLOCKS4 2
+#endif
+#ifndef NPSWF_VM_MAXN         // multiplicities with an analytic-path kernel; above: the exact Migrad kernels
+#define NPSWF_VM_MAXN 6
+#endif
 #ifndef NPSWF_VM_MINBLOCKS1   // single-pulse instance: 114 registers as it stands; a fourth CTA measures the same
 #define NPSWF_VM_MINBLOCKS1 3
 #endif
@@ -562,7 +576,7 @@ __device__ __forceinline__ void eval_vm(const double (&p)[2 * N + 1], const floa
 }
 
 template <int N>
-__global__ void __launch_bounds__(VM_THREADS, (N == 1) ? NPSWF_VM_MINBLOCKS1 : NPSWF_VM_MINBLOCKS)
+__global__ void __launch_bounds__(VM_THREADS, (N == 1) ? NPSWF_VM_MINBLOCKS1 : (N <= 3) ? NPSWF_VM_MINBLOCKS : NPSWF_VM_MINBLOCKS4)
 fit_vm_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_count, int *__restrict__ job_next,
                   const double *__restrict__ signal, const double *__restrict__ corr_time_HMS, DevCalib cal, KParams kp,
                   double *__restrict__ wftime, double *__restrict__ wfampl, double *__restrict__ chi2_out,
@@ -575,7 +589,7 @@ fit_vm_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ j
 #define NPSWF_VM_U2 1
 #define NPSWF_VM_U3 1
 #endif
-    constexpr int U = (N == 1) ? NPSWF_VM_U1 : (N == 2) ? NPSWF_VM_U2 : NPSWF_VM_U3;
+    constexpr int U = (N == 1) ? NPSWF_VM_U1 : (N == 2) ? NPSWF_VM_U2 : (N == 3) ? NPSWF_VM_U3 : 1;
     const unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char ft_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -81,7 +81,7 @@ struct DevSlot {
     bool fit_thread = true;     // thread-per-fit kernels for N = 1, 2 (env NPSWF_FIT_THREAD=0 selects the sub-warp kernels)
     int occ_fit_thread[5] = {0, 2, 2, 2, 2};   // [4]: N = 4..6
     int fit_thread_maxocc = 0;  // env NPSWF_FIT_THREAD_OCC: cap on resident CTAs per SM (fewer CTAs leave more L1)
-    int occ_vm_thread[4] = {0, 2, 2, 2};   // fit_vm_thread_kernel<1, 2, 3>
+    int occ_vm_thread[7] = {0, 2, 2, 2, 2, 2, 2};   // fit_vm_thread_kernel<1..6>
     int occ_migrad[3] = {2, 1, 1};   // fit_migrad_kernel<7, 13, 25>
     int occ_migrad_thread[4] = {0, 4, 4, 4};   // fit_migrad_thread_kernel<1, 2, 3>
     double *mg_wtab = nullptr;       // inverse error by |ADC count| (thread-per-fit Migrad kernels)
@@ -486,10 +486,10 @@ int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, cons
         const int *list = w.fit_dense + (size_t)N * stride;
         const int *cnt = w.fit_count + N;
         int *next = w.fit_count + 16 + N;  // per-multiplicity job cursor, zeroed with fit_count
-        const bool vm_fast = h->fit_mode == NPSWF_FIT_VM && N <= 3 && h->unit_knots && s.occ_vm_thread[N] > 0;
+        const bool vm_fast = h->fit_mode == NPSWF_FIT_VM && N <= NPSWF_VM_MAXN && h->unit_knots && s.occ_vm_thread[N] > 0;
         if (h->fit_mode == NPSWF_FIT_MIGRAD || (h->fit_mode == NPSWF_FIT_VM && !vm_fast)) {
             // the reference's own minimiser (Migrad, numerical gradients, strategy 1 -> 2), one warp per fit
-            // (VM mode: 4+ pulses and general knots have no analytic-path kernel and take the exact one)
+            // (VM mode: 7+ pulses and general knots have no analytic-path kernel and take the exact one)
             MigradArgs ma{list, cnt, next, N, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr};
             const int cls = migrad_class(N);
             if (N <= 3 && s.migrad_thread && s.occ_migrad_thread[N] > 0 && h->unit_knots) {
@@ -519,15 +519,22 @@ int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, cons
             int *ccnt = w.fit_count + 32 + N, *cnext = w.fit_count + 48 + N;
             int *clist = w.cont_list + (size_t)(N - 1) * stride;
             const int vgrid = s.sm_count * s.occ_vm_thread[N];
-            if (N == 1)
-                fit_vm_thread_kernel<1><<<vgrid, VM_THREADS, VM_SMEM, st>>>(list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2,
-                                                                            timewf, amplwf, status, s.ctr, ccnt, clist);
-            else if (N == 2)
-                fit_vm_thread_kernel<2><<<vgrid, VM_THREADS, VM_SMEM, st>>>(list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2,
-                                                                            timewf, amplwf, status, s.ctr, ccnt, clist);
-            else
-                fit_vm_thread_kernel<3><<<vgrid, VM_THREADS, VM_SMEM, st>>>(list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2,
-                                                                            timewf, amplwf, status, s.ctr, ccnt, clist);
+#define NPSWF_VM_LAUNCH(NN)                                                                                                    \
+    fit_vm_thread_kernel<NN><<<vgrid, VM_THREADS, VM_SMEM, st>>>(list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, \
+                                                                 timewf, amplwf, status, s.ctr, ccnt, clist)
+            switch (N) {
+            case 1: NPSWF_VM_LAUNCH(1); break;
+            case 2: NPSWF_VM_LAUNCH(2); break;
+            case 3: NPSWF_VM_LAUNCH(3); break;
+#if NPSWF_VM_MAXN >= 6
+            case 4: NPSWF_VM_LAUNCH(4); break;
+            case 5: NPSWF_VM_LAUNCH(5); break;
+            default: NPSWF_VM_LAUNCH(6); break;
+#else
+            default: break;
+#endif
+            }
+#undef NPSWF_VM_LAUNCH
             CU_TRY(h, cudaGetLastError());
             // the hand-over lists are short (~1 % of the fits): the warp-per-fit kernel finishes a fit in a fraction of a
             // millisecond, a thread of the thread-per-fit kernel needs 3-50 ms for one, which would be the tail of the stage
@@ -1292,12 +1299,16 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
         CR(cudaFuncSetAttribute(fit_thread_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
         CR(cudaFuncSetAttribute(fit_thread_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_thread[3], fit_thread_kernel<3>, FT_THREADS, FT_SMEM));
-        CR(cudaFuncSetAttribute(fit_vm_thread_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VM_SMEM));
-        CR(cudaFuncSetAttribute(fit_vm_thread_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VM_SMEM));
-        CR(cudaFuncSetAttribute(fit_vm_thread_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VM_SMEM));
-        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vm_thread[1], fit_vm_thread_kernel<1>, VM_THREADS, VM_SMEM));
-        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vm_thread[2], fit_vm_thread_kernel<2>, VM_THREADS, VM_SMEM));
-        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vm_thread[3], fit_vm_thread_kernel<3>, VM_THREADS, VM_SMEM));
+#define NPSWF_VM_SETUP(NN)                                                                                                   \
+    CR(cudaFuncSetAttribute(fit_vm_thread_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VM_SMEM));            \
+    CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vm_thread[NN], fit_vm_thread_kernel<NN>, VM_THREADS, VM_SMEM))
+        NPSWF_VM_SETUP(1); NPSWF_VM_SETUP(2); NPSWF_VM_SETUP(3);
+#if NPSWF_VM_MAXN >= 6
+        NPSWF_VM_SETUP(4); NPSWF_VM_SETUP(5); NPSWF_VM_SETUP(6);
+#else
+        s.occ_vm_thread[4] = s.occ_vm_thread[5] = s.occ_vm_thread[6] = 0;
+#endif
+#undef NPSWF_VM_SETUP
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_thread[1], fit_thread_kernel<1>, FT_THREADS, FT_SMEM));
         CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_thread[2], fit_thread_kernel<2>, FT_THREADS, FT_SMEM));
         if (getenv("NPSWF_FIT_THREAD_OCC")) s.fit_thread_maxocc = atoi(getenv("NPSWF_FIT_THREAD_OCC"));

@@ -272,10 +272,10 @@ def test_migrad_mode_through_every_entry_point(pkg, calib, spline):
 
 @pytest.mark.parametrize("cfg,acc,n_events,gate", [(1, 0.0, 200, 0.9999), (2, 0.0, 300, 0.9993), (2, -5.0, 100, 0.9990), (3, 0.0, 200, 0.990)])
 def test_vm_mode_follows_migrad(pkg, calib, spline, cfg, acc, n_events, gate):
-    """NPSWF_FIT_VM: Migrad's recursion with analytic derivatives (fit_vm_thread_kernel; exact kernels for 4+ pulses and
-    for what leaves the common path).  Everything that is not a fit result exact; fits within the BASELINE tolerances of
-    the oracle's Migrad on >= 99.93 % (1-3 pulses) / >= 99.0 % (up to 12 pulses near threshold) of the blocks where both
-    converge (measured: 99.989 % / 99.81 %), verdicts differing on < 0.05 % / < 0.3 %."""
+    """NPSWF_FIT_VM: Migrad's recursion with analytic derivatives (fit_vm_thread_kernel for 1-6 pulses; exact kernels for
+    7+ pulses and for what leaves the common path).  Everything that is not a fit result exact; fits within the BASELINE
+    tolerances of the oracle's Migrad on >= 99.93 % (1-3 pulses) / >= 99.0 % (up to 12 pulses near threshold) of the
+    blocks where both converge (measured: 99.989 % / 99.46 %), verdicts differing on < 0.05 % / < 0.3 %."""
     threads = os.cpu_count() or 1
     orc = oracle.Oracle(calib, timerefacc=acc)
     h = pkg.NpsWf(calib, timerefacc=acc, fit_mode=pkg.FIT_VM)
