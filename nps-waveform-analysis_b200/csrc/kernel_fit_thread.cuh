@@ -31,6 +31,33 @@ constexpr int FT_THREADS = FT_WARPS * 32;
 constexpr int FT_LD = 33;
 constexpr int FT_WARP_BYTES = NFIT * FT_LD * (int)sizeof(float2);   // (y, 1/err) per point
 constexpr size_t FT_SMEM = (size_t)FT_WARPS * FT_WARP_BYTES;         // 95 040 B -> 2 CTAs per SM
+// Instances with N <= NPSWF_FT_YONLY_MAXN keep the samples alone in the tile (47 520 B per CTA) and recompute the
+// weight 1 / Err per point on the FP32 / MUFU pipes -- bit for bit what inv_err_f32 stores, so the results do not
+// depend on the layout -- which lets NPSWF_FT_MINB<N> CTAs share an SM.  Measured (9 472 config-2 events, fit stage):
+// N = 1 at 3 CTAs / 168 registers 27.1 -> 26.5 ms (adopted); N = 2 as well: 27.1 (its spills land outside the point
+// loop, no gain); N = 1 at 4 CTAs / 128 registers with one point per loop body: 27.7; N = 3 at 3 CTAs: 29.9 (spills
+// inside the point loop).  The thread-per-fit kernels are bound by their FP64 instruction stream, not by latency.
+#ifndef NPSWF_FT_YONLY_MAXN
+#define NPSWF_FT_YONLY_MAXN 1
+#endif
+#ifndef NPSWF_FT_MINB1
+#define NPSWF_FT_MINB1 3
+#endif
+#ifndef NPSWF_FT_MINB2
+#define NPSWF_FT_MINB2 2
+#endif
+#ifndef NPSWF_FT_MINB3
+#define NPSWF_FT_MINB3 2
+#endif
+#ifndef NPSWF_FT_U1
+#define NPSWF_FT_U1 5
+#endif
+__host__ __device__ constexpr bool ft_yonly(int N) { return N <= NPSWF_FT_YONLY_MAXN; }
+__host__ __device__ constexpr int ft_warp_bytes(int N) { return ft_yonly(N) ? (NFIT * FT_LD * (int)sizeof(float) + 15) / 16 * 16 : FT_WARP_BYTES; }
+__host__ __device__ constexpr size_t ft_smem(int N) { return (size_t)FT_WARPS * ft_warp_bytes(N); }
+__host__ __device__ constexpr int ft_minblocks(int N) { return N == 1 ? NPSWF_FT_MINB1 : N == 2 ? NPSWF_FT_MINB2 : N == 3 ? NPSWF_FT_MINB3 : 2; }
+template <bool YONLY> struct FtTile { typedef float2 type; };
+template <> struct FtTile<true> { typedef float type; };
 constexpr int FT_CONT_STRIDE = 10;  // doubles per continuation record: par[P] | lambda | iters << 7 | rejects << 1 | newton
 
 // 1 / Err (T2:946-956) as the binary32 weight the kernel stores: the same branch point as inv_err(), the
@@ -45,13 +72,27 @@ __device__ __forceinline__ float inv_err_f32(double v)
     return (a < 0x1.0624dd2f1a9fcp+3) ? 0x1.6e5b7ep+1f : wv;
 }
 
+// sample and weight of one tile entry: stored pair, or the weight recomputed from the (binary32-exact) sample
+__device__ __forceinline__ void ft_point(const float2 e, double &y, double &w) { y = (double)e.x; w = (double)e.y; }
+__device__ __forceinline__ void ft_point(const float e, double &y, double &w)
+{
+    const float af = fabsf(e);
+    float rs;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(af));
+    const float wf = (af < 0x1.0624dep+3f) ? 0x1.6e5b7ep+1f : rs * 0x1.6e5b7ep+1f;   // = inv_err_f32((double)e)
+    y = (double)e;
+    w = (double)wf;
+}
+__device__ __forceinline__ void ft_store(float2 *dst, float yf, double v) { *dst = make_float2(yf, inv_err_f32(v)); }
+__device__ __forceinline__ void ft_store(float *dst, float yf, double) { *dst = yf; }
+
 // chi2 and normal equations of one fit at parameters p, all 90 points, one thread.
 // kn points at knot 0 of the block's zero-padded knot array.  U points per loop body; the loads of the next
 // body are issued before the arithmetic of the current one.
 // DIAG: only the diagonal of the normal matrix is accumulated (the variable-metric kernel needs chi2, its gradient and
 // its second derivatives along the axes, not the full Gauss-Newton matrix).
-template <int N, int U, bool DIAG = false>
-__device__ __forceinline__ void eval_thread(const double (&p)[2 * N + 1], const float2 *__restrict__ ywcol,
+template <int N, int U, bool DIAG = false, typename TY = float2>
+__device__ __forceinline__ void eval_thread(const double (&p)[2 * N + 1], const TY *__restrict__ ywcol,
                                             const double2 *__restrict__ kn, NormalEq<2 * N + 1> &ne)
 {
     constexpr int P = 2 * N + 1;
@@ -93,9 +134,9 @@ __device__ __forceinline__ void eval_thread(const double (&p)[2 * N + 1], const 
     for (int n = 0; n < N; n++) { ne.s1[n] = 0; ne.s2[n] = 0; }
     const double p0 = p[0];
     // two register buffers of U points each: while one is consumed the other is being loaded (no copies)
-    float2 ywA[U], ywB[U];
+    TY ywA[U], ywB[U];
     double2 kA[N][U], kB[N][U];
-    auto load = [&](int jb, float2 (&yw)[U], double2 (&kk)[N][U]) {
+    auto load = [&](int jb, TY (&yw)[U], double2 (&kk)[N][U]) {
 #pragma unroll
         for (int u = 0; u < U; u++) {
             yw[u] = ywcol[(jb + u) * FT_LD];
@@ -103,12 +144,13 @@ __device__ __forceinline__ void eval_thread(const double (&p)[2 * N + 1], const 
             for (int n = 0; n < N; n++) kk[n][u] = __ldg(kp[n] + jb + u + 1);
         }
     };
-    auto consume = [&](int jb, const float2 (&yw)[U], const double2 (&kk)[N][U]) {
+    auto consume = [&](int jb, const TY (&yw)[U], const double2 (&kk)[N][U]) {
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int j = jb + u;
-            const double wk = (double)yw[u].y;
-            double r = ((double)yw[u].x - p0) * wk;
+            double wk, yv;
+            ft_point(yw[u], yv, wk);
+            double r = (yv - p0) * wk;
             double J[P];
             double dsw[N], d2w[N];
             J[0] = wk;
@@ -171,7 +213,7 @@ __device__ __forceinline__ void eval_thread(const double (&p)[2 * N + 1], const 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int N>
-__global__ void __launch_bounds__(FT_THREADS, 2)
+__global__ void __launch_bounds__(FT_THREADS, ft_minblocks(N))
 fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_count, int *__restrict__ job_next,
                   const double *__restrict__ signal, const double *__restrict__ corr_time_HMS, DevCalib cal, KParams kp,
                   double *__restrict__ wftime, double *__restrict__ wfampl, double *__restrict__ chi2_out,
@@ -180,13 +222,14 @@ fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
                   double *__restrict__ cont_state)
 {
     constexpr int P = 2 * N + 1;
-    constexpr int U = (N == 1) ? 5 : 1;
+    constexpr int U = (N == 1) ? NPSWF_FT_U1 : 1;
     constexpr double REL_TOL = FIT_REL_TOL;
+    typedef typename FtTile<ft_yonly(N)>::type TY;
     const unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char ft_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float2 *ywwarp = reinterpret_cast<float2 *>(ft_smem + (size_t)warp * FT_WARP_BYTES);   // [90][33] (sample, 1/err)
-    const float2 *ywcol = ywwarp + lane;
+    TY *ywwarp = reinterpret_cast<TY *>(ft_smem + (size_t)warp * ft_warp_bytes(N));   // [90][33] (sample, 1/err) or samples
+    const TY *ywcol = ywwarp + lane;
     const int njobs = *job_count;
     // N >= 4 has no sub-warp continuation kernel that could take over the LM state: a fit that is not done after
     // fit_thread_tries + 10 tries (a thread's try takes ~30x as long as a warp's, and these kernels have few jobs, so
@@ -277,7 +320,7 @@ fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
                         if (c >= MFSTART && c < MFEND && its[k] >= 0) {
                             const float yf = (float)v[k][c4];
                             exact = exact && ((double)yf == v[k][c4]) && (fabsf(yf) <= 3.0e38f);   // NaN fails the first test, +-Inf the second
-                            ywwarp[(c - MFSTART) * FT_LD + ls[k]] = make_float2(yf, inv_err_f32(v[k][c4]));
+                            ft_store(&ywwarp[(c - MFSTART) * FT_LD + ls[k]], yf, v[k][c4]);
                         }
                     }
                     exact = __all_sync(FULL, exact);
@@ -314,7 +357,7 @@ fit_thread_kernel(const int *__restrict__ job_list, const int *__restrict__ job_
         // whose bound is below the tolerance is not worth its evaluation
         const bool pre_done = has_job && !fresh && pd && lambda <= 1e-2 && lm_pred2<P>(cur, dp) < REL_TOL * (fabs(cur.c2) + 1e-30);
         NormalEq<P> nxt;
-        eval_thread<N, U>(trial, ywcol, kn, nxt);
+        eval_thread<N, U, false, TY>(trial, ywcol, kn, nxt);
         bool finished = pre_done, handoff = false;
         if (has_job && !pre_done) {
             tries++;

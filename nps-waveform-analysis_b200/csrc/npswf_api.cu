@@ -556,19 +556,19 @@ int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, cons
             double *cstate = w.cont_state + (size_t)(N - 1) * stride * FT_CONT_STRIDE;
             const int tgrid = s.sm_count * s.occ_fit_thread[N], sgrid = s.sm_count * 3;
             if (N == 1) {
-                fit_thread_kernel<1><<<tgrid, FT_THREADS, FT_SMEM, st>>>(
+                fit_thread_kernel<1><<<tgrid, FT_THREADS, ft_smem(1), st>>>(
                     list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, ccnt, clist, cstate);
                 CU_TRY(h, cudaGetLastError());
                 fit_small_kernel<1, 16, 3><<<sgrid, FS_THREADS, 0, st>>>(
                     clist, ccnt, cnext, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, cstate);
             } else if (N == 2) {
-                fit_thread_kernel<2><<<tgrid, FT_THREADS, FT_SMEM, st>>>(
+                fit_thread_kernel<2><<<tgrid, FT_THREADS, ft_smem(2), st>>>(
                     list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, ccnt, clist, cstate);
                 CU_TRY(h, cudaGetLastError());
                 fit_small_kernel<2, 16, 3><<<sgrid, FS_THREADS, 0, st>>>(
                     clist, ccnt, cnext, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, cstate);
             } else {
-                fit_thread_kernel<3><<<tgrid, FT_THREADS, FT_SMEM, st>>>(
+                fit_thread_kernel<3><<<tgrid, FT_THREADS, ft_smem(3), st>>>(
                     list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl, chi2, timewf, amplwf, status, s.ctr, ccnt, clist, cstate);
                 CU_TRY(h, cudaGetLastError());
                 fit_small_kernel<3, 16, FS_MINB3><<<s.sm_count * s.occ_fit_small[3], FS_THREADS, 0, st>>>(
@@ -581,13 +581,13 @@ int launch_fits(npswf_handle *h, DevSlot &s, cudaStream_t st, Workspace &w, cons
             int *clist = w.cont_list + (size_t)(N - 1) * stride;
             const int tgrid = s.sm_count * s.occ_fit_thread[4];
             if (N == 4)
-                fit_thread_kernel<4><<<tgrid, FT_THREADS, FT_SMEM, st>>>(list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl,
+                fit_thread_kernel<4><<<tgrid, FT_THREADS, ft_smem(4), st>>>(list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl,
                                                                         chi2, timewf, amplwf, status, s.ctr, ccnt, clist, nullptr);
             else if (N == 5)
-                fit_thread_kernel<5><<<tgrid, FT_THREADS, FT_SMEM, st>>>(list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl,
+                fit_thread_kernel<5><<<tgrid, FT_THREADS, ft_smem(5), st>>>(list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl,
                                                                         chi2, timewf, amplwf, status, s.ctr, ccnt, clist, nullptr);
             else
-                fit_thread_kernel<6><<<tgrid, FT_THREADS, FT_SMEM, st>>>(list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl,
+                fit_thread_kernel<6><<<tgrid, FT_THREADS, ft_smem(6), st>>>(list, cnt, next, sig, corr, s.cal, h->kp, wftime, wfampl,
                                                                         chi2, timewf, amplwf, status, s.ctr, ccnt, clist, nullptr);
             CU_TRY(h, cudaGetLastError());
             // P <= 13: half the shared memory of the 25-parameter instance, twice the resident warps; jobs claimed one by one
@@ -1292,13 +1292,13 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
         if ((rc = dev_alloc(h, s, &s.mg_wtab, (size_t)MIGRAD_WTAB_ENTRIES))) return fail(rc);
         if (s.occ_migrad[0] < 1 || s.occ_migrad[1] < 1 || s.occ_migrad[2] < 1) { h->err = "fit_migrad_kernel does not fit on this device"; return fail(NPSWF_ERR_CUDA); }
         s.fit_thread = !(getenv("NPSWF_FIT_THREAD") && atoi(getenv("NPSWF_FIT_THREAD")) == 0);
-        CR(cudaFuncSetAttribute(fit_thread_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
-        CR(cudaFuncSetAttribute(fit_thread_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
-        CR(cudaFuncSetAttribute(fit_thread_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
-        CR(cudaFuncSetAttribute(fit_thread_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
-        CR(cudaFuncSetAttribute(fit_thread_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
-        CR(cudaFuncSetAttribute(fit_thread_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
-        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_thread[3], fit_thread_kernel<3>, FT_THREADS, FT_SMEM));
+        CR(cudaFuncSetAttribute(fit_thread_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ft_smem(1)));
+        CR(cudaFuncSetAttribute(fit_thread_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ft_smem(2)));
+        CR(cudaFuncSetAttribute(fit_thread_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ft_smem(3)));
+        CR(cudaFuncSetAttribute(fit_thread_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ft_smem(4)));
+        CR(cudaFuncSetAttribute(fit_thread_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ft_smem(5)));
+        CR(cudaFuncSetAttribute(fit_thread_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ft_smem(6)));
+        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_thread[3], fit_thread_kernel<3>, FT_THREADS, ft_smem(3)));
 #define NPSWF_VM_SETUP(NN)                                                                                                   \
     CR(cudaFuncSetAttribute(fit_vm_thread_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VM_SMEM));            \
     CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vm_thread[NN], fit_vm_thread_kernel<NN>, VM_THREADS, VM_SMEM))
@@ -1309,8 +1309,8 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
         s.occ_vm_thread[4] = s.occ_vm_thread[5] = s.occ_vm_thread[6] = 0;
 #endif
 #undef NPSWF_VM_SETUP
-        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_thread[1], fit_thread_kernel<1>, FT_THREADS, FT_SMEM));
-        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_thread[2], fit_thread_kernel<2>, FT_THREADS, FT_SMEM));
+        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_thread[1], fit_thread_kernel<1>, FT_THREADS, ft_smem(1)));
+        CR(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_fit_thread[2], fit_thread_kernel<2>, FT_THREADS, ft_smem(2)));
         if (getenv("NPSWF_FIT_THREAD_OCC")) s.fit_thread_maxocc = atoi(getenv("NPSWF_FIT_THREAD_OCC"));
         if (s.fit_thread_maxocc > 0) {
             for (int n = 1; n <= 3; n++) s.occ_fit_thread[n] = std::min(s.occ_fit_thread[n], s.fit_thread_maxocc);
