@@ -192,6 +192,13 @@ int64_t npswf_event_times(const int32_t *wfnpulse, const double *wftime_padded, 
  * number, 3 above the EDM limit, 4 not a descent direction), since the last reset (device 0). */
 int npswf_debug_vm_reasons(npswf_handle *h, uint64_t out[8], int reset);
 
+/* Diagnostics of the peak search (TSpectrum::SearchHighRes, T2:187-188): out[0] = spectra whose Gold deconvolution was
+ * evaluated with fused multiply-adds and every decision (iteration gates, local maxima, thresholds, integer parts of
+ * the centroids) checked against the error margin of that evaluation; out[1] = of those, the spectra with a decision
+ * inside the margin, which were repeated with the reference's arithmetic (rounded product, rounded sum).  Summed over
+ * the handle's devices since the last reset. */
+int npswf_debug_search_fused(npswf_handle *h, uint64_t out[2], int reset);
+
 /* Measured rate of the raw binary64 uploads out of the caller's pinned buffers (CUDA events around the raw part of a
  * chunk, running mean over the devices; 48 until something was measured), and the number of host cores the packer
  * threads / staging buffers are confined to (the cores of each GPU's NUMA node, from sysfs; 0 = topology not visible

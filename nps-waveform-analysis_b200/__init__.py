@@ -59,6 +59,7 @@ EXPORTS = [
     "npswf_event_diagnostics_batch", "npswf_event_diagnostics_device", "npswf_set_profiling",
     "npswf_get_stage_times", "npswf_set_host_packing", "npswf_host_packing_stats", "npswf_debug_pack_counts", "npswf_analyze_batch_flat",
     "npswf_analyze_batch_flat_i16", "npswf_host_upload_rate", "npswf_hcana_pulses", "npswf_event_times", "npswf_debug_vm_reasons",
+    "npswf_debug_search_fused",
 ]
 
 _lib = None
@@ -250,6 +251,12 @@ class NpsWf:
         out = np.zeros(8, np.uint64)
         self._check(lib().npswf_debug_vm_reasons(self.h, _p(out), C.c_int(1 if reset else 0)))
         return [int(v) for v in out]
+
+    def search_fused(self, reset=True):
+        """(spectra deconvolved with the fused evaluation, of those repeated with the reference's arithmetic); npswf.h."""
+        out = np.zeros(2, np.uint64)
+        self._check(lib().npswf_debug_search_fused(self.h, _p(out), C.c_int(1 if reset else 0)))
+        return int(out[0]), int(out[1])
 
     def host_upload_rate(self):
         """(measured GB/s of the raw binary64 uploads, host cores the transport threads are bound to)."""

@@ -1986,6 +1986,27 @@ int npswf_debug_vm_reasons(npswf_handle *h, uint64_t out[8], int reset)
     return 0;
 }
 
+int npswf_debug_search_fused(npswf_handle *h, uint64_t out[2], int reset)
+{
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (!out) return NPSWF_ERR_ARG;
+    out[0] = out[1] = 0;
+    for (size_t d = 0; d < h->slots.size(); d++) {
+        CU_TRY(h, cudaSetDevice(h->slots[d].device));
+        CU_TRY(h, cudaDeviceSynchronize());
+        unsigned long long tmp[2];
+        CU_TRY(h, cudaMemcpyFromSymbol(tmp, g_search_fused, sizeof tmp));
+        out[0] += tmp[0];
+        out[1] += tmp[1];
+        if (reset) {
+            unsigned long long z[2] = {0, 0};
+            CU_TRY(h, cudaMemcpyToSymbol(g_search_fused, z, sizeof z));
+        }
+    }
+    return 0;
+}
+
 int npswf_get_mf_calib(const npswf_handle *h, double *mfyref, double *mfint)
 {
     if (!h || !mfyref || !mfint) return NPSWF_ERR_ARG;

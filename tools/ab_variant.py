@@ -70,6 +70,7 @@ def main():
     h.sync_device(stream=st)
     t = h.stage_times()
     c = h.counters()
+    fz = h.search_fused() if hasattr(h, "search_fused") else (0, 0)
     h.set_profiling(False)
     torch.cuda.synchronize()
     walls = []
@@ -82,9 +83,9 @@ def main():
         h.sync_device(stream=st)
         torch.cuda.synchronize()
         walls.append(e0.elapsed_time(e1) / K)
-    print("AB %-8s cfg2 x %d: front %.3f search %.3f fit %.3f ms | overlapped step %.3f ms (best of 3: %s) | evals/fit %.2f cont %d" % (
+    print("AB %-8s cfg2 x %d: front %.3f search %.3f fit %.3f ms | overlapped step %.3f ms (best of 3: %s) | evals/fit %.2f | search fused %d redone %d" % (
         tag, E, t["front_ms"] / K, t["search_ms"] / K, t["fit_ms"] / K, min(walls), " ".join("%.2f" % w for w in walls),
-        c["n_fit_evals"] / max(1, c["n_fit_attempted"]), c.get("n_fit_handed_over", -1)), flush=True)
+        c["n_fit_evals"] / max(1, c["n_fit_attempted"]), fz[0], fz[1]), flush=True)
 
 
 if __name__ == "__main__":
