@@ -293,7 +293,8 @@ int npswf_debug_exp(npswf_handle *h, int64_t n, const double *x, double *y);
 /* Bit-exactness tap: the search kernel inlines the refinement chains of IEEE division / square root without
  * the out-of-range slow path.  Runs >= n_trials device-generated operand pairs of the Markov-step domain
  * through both and counts results that differ from __ddiv_rn / __dsqrt_rn:
- * mismatch[0] = b / sqrt(s) chain, mismatch[1] = a / b chain.  Both must be 0. */
+ * mismatch[0] = b / sqrt(s) chain, mismatch[1] = a / b chain (plus the quotients of the fused deconvolution pass'
+ * approximate division that are more than 2 ulp off).  Both must be 0. */
 int npswf_debug_exact_ops(npswf_handle *h, int64_t n_trials, uint64_t seed, uint64_t mismatch[2]);
 
 /* Measurement tap: FP64 FMA throughput of device 0 (GFLOP/s, FMA = 2 flop) from a register-resident chain

@@ -58,6 +58,7 @@ def main():
         torch.cuda.synchronize()
         np.savez("/tmp/ab_%s_cfg%d.npz" % (tag, cfg), **{k: v.cpu().numpy() for k, v in o.items()})
         del sig, pres, corr, o
+    print("AB %-8s inlined division / square-root chains vs IEEE (mismatches, must be 0 0):" % tag, h.debug_exact_ops(400_000_000, seed=11), flush=True)
     E = 9472
     sig, pres, corr, o = batch(E, 2)
     h.set_profiling(True)
