@@ -132,6 +132,61 @@ def test_find_pulses_exact(gpu, orc, events, cfg):
             assert (t[e, b, on:] == -999).all() and (a[e, b, on:] == -999).all()
 
 
+def test_search_fused_pass_equals_reference_arithmetic(pkg, calib, orc, monkeypatch):
+    """The peak search deconvolves with FMA chains first and repeats a spectrum with the reference's arithmetic
+    (rounded product, rounded sum) when a decision lies inside the error margin of that evaluation
+    (kernel_search.cuh, gold_block).  Three handles -- exact arithmetic only, the default, and the fused pass
+    followed by the exact repeat for EVERY spectrum -- must return the same bits: peak count, order, times
+    (integer bins), amplitudes.  Inputs: pile-up near threshold (config 3), 1-3 pulses (config 2), and traces
+    built to stress the margins: huge pulses on a quiet baseline (deconvolved tails near the 1e-5 gates of the
+    Gold iteration), equal twin pulses (ties between neighbouring channels), plateaus, scaled copies."""
+    rng = np.random.default_rng(23)
+    sets = []
+    for cfg, n_ev in ((3, 6), (2, 6)):
+        ev = synth.generate_host(synth.config_params(cfg), orc.spline_coeffs(), calib, 40 + cfg, n_ev, n_threads=4)
+        sets.append((ev["signal"], ev["pres"]))
+    sig = rng.normal(0.0, 0.3, (4, 1080, 110))
+    lsb = 1000.0 / 4096.0
+    shape = np.exp(-0.5 * ((np.arange(110)[None, :] - 45.0) / 3.0) ** 2)
+    amp = 10.0 ** rng.uniform(0.5, 4.0, (1080, 1))
+    sig[0] += amp * shape                                                         # 3 mV .. 10 V single pulses
+    sig[1] += amp * (shape + np.roll(shape, 12, axis=1))                          # equal twins 12 bins apart
+    sig[2] = np.round((amp * np.clip(shape * 3.0, 0, 1.0)) / lsb) * lsb            # noise-free plateaus on the ADC lattice
+    sig[3] = sig[0] * rng.choice([0.25, 0.5, 2.0, 4.0], (1080, 1))                # power-of-two copies
+    sets.append((sig, np.ones((4, 1080), np.int32)))
+    results = {}
+    for mode in (0, 1, 2):
+        monkeypatch.setenv("NPSWF_SEARCH_FUSED", str(mode))
+        h = pkg.NpsWf(calib)
+        h.search_fused(reset=True)
+        results[mode] = [h.FindPulsesMF(s_, p_) for s_, p_ in sets]
+        fused, redone = h.search_fused(reset=True)
+        if mode == 0:
+            assert fused == 0
+        elif mode == 1:
+            assert fused > 10000 and redone <= 0.02 * fused, (fused, redone)
+        else:
+            assert fused > 10000 and redone == fused
+        h.close()
+    monkeypatch.delenv("NPSWF_SEARCH_FUSED")
+    n_peaks = 0
+    for k in range(len(sets)):
+        for mode in (1, 2):
+            for x, y in zip(results[0][k], results[mode][k]):
+                assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), (k, mode)
+        n_peaks += int(results[0][k][0].sum())
+    assert n_peaks > 20000
+    # and the exact-arithmetic handle against the oracle on the stress set
+    n, t, a = results[0][2]
+    s_, p_ = sets[2]
+    for e in range(s_.shape[0]):
+        for b in range(0, 1080, 5):
+            on, ot, oa = orc.find_pulses_mf(b, s_[e], p_[e])
+            assert n[e, b] == on, (e, b)
+            if on:
+                assert np.array_equal(t[e, b, :on], ot[:on]) and np.array_equal(a[e, b, :on], oa[:on]), (e, b)
+
+
 @pytest.mark.parametrize("cfg", [1, 2, 3])
 def test_cluster_threshold_exact(gpu, orc, events, cfg):
     ev = events[cfg]
