@@ -16,8 +16,12 @@
 
 namespace npswf {
 
-constexpr int FRONT_THREADS = 256;
-constexpr int FRONT_WARPS = FRONT_THREADS / 32;
+#ifndef NPSWF_FRONT_WARPS   // 8 (128 registers) or 10 (96 registers: three rounds of ten column tasks instead of four of eight)
+#define NPSWF_FRONT_WARPS 8
+#endif
+constexpr int FRONT_WARPS = NPSWF_FRONT_WARPS;
+constexpr int FRONT_THREADS = FRONT_WARPS * 32;
+static_assert(FRONT_WARPS == 8 || FRONT_WARPS == 10 || FRONT_WARPS == 12, "the per-row task dealing below is written for 8, 10 or 12 warps");
 constexpr int FRONT_RING = 4;
 constexpr size_t FRONT_SMEM = (size_t)FRONT_RING * ROW_BYTES + 64 /*mbarriers*/ + 1088 /*pres bytes*/ + 16 + 1024 /*zero trace*/ +
                               2 * 3 * 32 * sizeof(int) /*neighbour offset tables of two rows*/;
@@ -250,8 +254,12 @@ front_kernel(const double *__restrict__ signal, const int32_t *__restrict__ pres
             }
             // 30 warp tasks.  The matched filter gave warps 0-6 two block pairs and warp 7 one, so the columns are dealt
             // 4-4-4-4-3-3-3-5: every warp ends the row with about the same number of instructions
-            const int c_first = (warp < 4) ? 4 * warp : ((warp < 7) ? 16 + 3 * (warp - 4) : 25);
-            const int c_count = (warp < 4) ? 4 : ((warp < 7) ? 3 : 5);
+            // (ten warps: warps 0-4 had two block pairs and take two columns each, warps 5-9 had one and take four)
+            const int c_first = (FRONT_WARPS == 12) ? ((warp < 3) ? warp : 3 + 3 * (warp - 3))
+                              : (FRONT_WARPS == 10) ? ((warp < 5) ? 2 * warp : 10 + 4 * (warp - 5))
+                                                    : ((warp < 4) ? 4 * warp : ((warp < 7) ? 16 + 3 * (warp - 4) : 25));
+            const int c_count = (FRONT_WARPS == 12) ? ((warp < 3) ? 1 : 3)
+                              : (FRONT_WARPS == 10) ? ((warp < 5) ? 2 : 4) : ((warp < 4) ? 4 : ((warp < 7) ? 3 : 5));
             for (int col = c_first; col < c_first + c_count; col++) {
                 const int bn = r * NCOL + col;
                 const bool present = (pres1[bn] & 2) != 0;
