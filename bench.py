@@ -478,14 +478,14 @@ def main():
     dom = max(("front", "search", "fit"), key=lambda k: stages[k + "_ms"])
     launches_per_chunk = {"front": 1, "search": 1, "fit": 14}
     # dram__bytes_read.sum + dram__bytes_write.sum per block-waveform, from the `ncu --set full` capture of this round's
-    # build (profiles/r2_ncu_full_search_front.csv: launches of 1 184 events = 1 278 720 block-waveforms)
-    ncu_traffic_per_unit = {"front": (1.132483e9 + 539.487e6) / 1278720.0, "search": (1.799129e9 + 292.069e6) / 1278720.0}
+    # final build (profiles/r2c_ncu_full_search_front_fit.csv: launches of 1 184 events = 1 278 720 block-waveforms)
+    ncu_traffic_per_unit = {"front": (1.132395e9 + 539.443e6) / 1278720.0, "search": (0.914046e9 + 280.581e6) / 1278720.0}
     units_per_launch = units_local / chunks
     traffic = ncu_traffic_per_unit[dom] * units_per_launch if dom in ncu_traffic_per_unit else None
     roofline = {"kernel": {"front": "front_kernel", "search": "search_kernel", "fit": "fit_thread_kernel<1,2> + fit_small_kernel + fit_kernel<25> (14 launches)"}[dom],
                 "bound": "hbm", "achieved": stage_rows[dom]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
                 "frac": stage_rows[dom]["achieved_gbs"] / hbm, "traffic": traffic,
-                "traffic_source": "ncu --set full, profiles/r2_ncu_full_search_front.csv (bytes per block-waveform x block-waveforms per launch)",
+                "traffic_source": "ncu --set full, profiles/r2c_ncu_full_search_front_fit.csv (bytes per block-waveform x block-waveforms per launch)",
                 "peak_source": peak_src,
                 "note": "dominant stage is FP64-pipe bound, not HBM bound (bit-faithful FP64 TSpectrum / FP64 LM); "
                         "see stages, fp64_peak_gflops_measured and DESIGN.md",
@@ -498,7 +498,11 @@ def main():
         ops_unit = 39000.0
         ach = stage_rows["search"]["units_per_s"] * ops_unit / 1e12
         roofline["fp64"] = {"ops_per_unit": ops_unit, "achieved_tops": ach, "peak_tops": fp64_peak / 2e3,
-                            "frac": ach / (fp64_peak / 2e3), "unit": "T FP64 instr-lanes/s"}
+                            "frac": ach / (fp64_peak / 2e3), "unit": "T FP64 instr-lanes/s",
+                            "note": "ops_per_unit = FP64 operations of the reference's arithmetic (SearchHighRes as ROOT runs it); the "
+                                    "kernel's fused pass executes 915 FP64 warp-instructions (25 000 lane-operations) per spectrum for "
+                                    "them (ncu, profiles/r2c_source_lines_search.txt: FP64 pipe 41.7 %, issue slots 66.9 %) and repeats "
+                                    "0.02 % of the spectra with the exact arithmetic"}
     # fit-stage arithmetic: SURVEY §8(d) flops_iter(N) with the mean multiplicity
     n_mean = pulses / max(1, fitted)
     Pm = 1 + 2 * n_mean
