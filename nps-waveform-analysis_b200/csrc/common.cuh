@@ -143,7 +143,8 @@ struct KParams {
     int fit_max_iter, fit_retry_max_iter;
     int fit_thread_tries;   // LM tries the thread-per-fit kernel runs before handing a fit to the sub-warp kernel
     int search_fused;       // Gold deconvolution of the peak search: 1 fused pass with checked decisions (default), 0 the
-                            // reference's arithmetic only, 2 fused pass and then always the exact repeat (env NPSWF_SEARCH_FUSED; test aid)
+                            // reference's arithmetic only, 2 fused pass and then always the exact repeat, 3 as 1 but the debug
+                            // taps show the unchecked fused pass (env NPSWF_SEARCH_FUSED; test aids)
 };
 
 }  // namespace npswf

@@ -1082,7 +1082,7 @@ int npswf_create(const NpsWfConfig *cfg, const NpsWfCalib *cal, npswf_handle **o
     h->kp.dt = cfg->dt; h->kp.timerefacc = cfg->timerefacc; h->kp.coinc_width = cfg->coinc_width;
     h->kp.fit_max_iter = cfg->fit_max_iter > 0 ? cfg->fit_max_iter : 60;
     h->kp.fit_retry_max_iter = cfg->fit_retry_max_iter > 0 ? cfg->fit_retry_max_iter : 100;
-    h->kp.search_fused = getenv("NPSWF_SEARCH_FUSED") ? std::max(0, std::min(2, atoi(getenv("NPSWF_SEARCH_FUSED")))) : 1;
+    h->kp.search_fused = getenv("NPSWF_SEARCH_FUSED") ? std::max(0, std::min(3, atoi(getenv("NPSWF_SEARCH_FUSED")))) : 1;
     h->kp.fit_thread_tries = (getenv("NPSWF_FIT_THREAD_TRIES") && atoi(getenv("NPSWF_FIT_THREAD_TRIES")) > 0) ? atoi(getenv("NPSWF_FIT_THREAD_TRIES")) : 20;
     h->fit_mode = (cfg->fit_mode == NPSWF_FIT_MIGRAD || cfg->fit_mode == NPSWF_FIT_VM) ? cfg->fit_mode : NPSWF_FIT_FAST;
     if (getenv("NPSWF_FIT_MODE")) {   // A/B runs of unchanged callers
