@@ -500,8 +500,8 @@ def main():
         roofline["fp64"] = {"ops_per_unit": ops_unit, "achieved_tops": ach, "peak_tops": fp64_peak / 2e3,
                             "frac": ach / (fp64_peak / 2e3), "unit": "T FP64 instr-lanes/s",
                             "note": "ops_per_unit = FP64 operations of the reference's arithmetic (SearchHighRes as ROOT runs it); the "
-                                    "kernel's fused pass executes 915 FP64 warp-instructions (25 000 lane-operations) per spectrum for "
-                                    "them (ncu, profiles/r2c_source_lines_search.txt: FP64 pipe 41.7 %, issue slots 66.9 %) and repeats "
+                                    "kernel's fused pass executes 893 FP64 warp-instructions (24 500 lane-operations) per spectrum for "
+                                    "them (ncu, profiles/r2d_source_lines_search.txt: FP64 pipe 41.8 %, issue slots 65.9 %) and repeats "
                                     "0.02 % of the spectra with the exact arithmetic"}
     # fit-stage arithmetic: SURVEY §8(d) flops_iter(N) with the mean multiplicity
     n_mean = pulses / max(1, fitted)
