@@ -50,7 +50,8 @@ def test_no_cpu_fallback(pkg, calib):
     sig = np.zeros((1, 1080, 110)); pres = np.ones((1, 1080), np.int32)
     for call in (lambda: h.analyze(sig, pres, np.zeros(1)), lambda: h.FindPulsesMF(sig, pres),
                  lambda: h.PassClusterThreshold(sig, pres), lambda: h.matched_filter(sig, pres),
-                 lambda: h.tspectrum_debug(np.zeros((1, 110), np.float32))):
+                 lambda: h.tspectrum_debug(np.zeros((1, 110), np.float32)), lambda: h.search_fused(),
+                 lambda: h.debug_exact_ops(1000)):
         with pytest.raises(pkg.NpsWfError) as ei:
             call()
         assert ei.value.code == pkg.ERR_CUDA
