@@ -188,8 +188,8 @@ def test_search_fused_pass_equals_reference_arithmetic(pkg, calib, orc, monkeypa
 
 
 def test_search_fused_pass_stays_inside_its_error_budget(pkg, calib, gpu, orc, monkeypatch):
-    """The budget behind the fused pass (kernel_search.cuh, gold_block): smoothed spectrum within 12 748 u, deconvolved
-    spectrum within 89 621 u = 2^-36.5 of the reference's arithmetic (u = 2^-53), against decision margins of 2^-22.
+    """The budget behind the fused pass (kernel_search.cuh, gold_block): smoothed spectrum within 24 258 u, deconvolved
+    spectrum within 170 200 u = 2^-35.6 of the reference's arithmetic (u = 2^-53), against decision margins of 2^-22.
     NPSWF_SEARCH_FUSED=3 makes the debug taps show the unchecked fused pass; the default handle's taps are the exact
     arithmetic (bitwise equal to the oracle, test_tspectrum_intermediates_bit_exact)."""
     ev = synth.generate_host(synth.config_params(3), orc.spline_coeffs(), calib, 77, 2, n_threads=4)
@@ -205,14 +205,14 @@ def test_search_fused_pass_stays_inside_its_error_budget(pkg, calib, gpu, orc, m
     h3.close()
     u = 2.0 ** -53
     worst = {}
-    for name, x0, x3, budget in (("smoothed", s0, s3, 12748 * u), ("deconvolved", d0, d3, 89621 * u)):
+    for name, x0, x3, budget in (("smoothed", s0, s3, 24258 * u), ("deconvolved", d0, d3, 170200 * u)):
         assert np.array_equal(x0 == 0, x3 == 0), name   # the zero pattern
         nz = x0 != 0
         rel = np.abs(x3[nz] - x0[nz]) / np.abs(x0[nz])
         worst[name] = float(rel.max())
         assert rel.max() <= budget, (name, rel.max() / u)
-    print("fused pass vs exact arithmetic on %d spectra: smoothed spectrum max %.0f u (budget 12 748), deconvolved max %.0f u "
-          "(budget 89 621), peak counts equal on %d" % (len(mf), worst["smoothed"] / u, worst["deconvolved"] / u, int((n0 == n3).sum())))
+    print("fused pass vs exact arithmetic on %d spectra: smoothed spectrum max %.0f u (budget 24 258), deconvolved max %.0f u "
+          "(budget 170 200), peak counts equal on %d" % (len(mf), worst["smoothed"] / u, worst["deconvolved"] / u, int((n0 == n3).sum())))
     assert (n0 == n3).mean() > 0.999   # unchecked, so a spectrum with a decision inside the margin may differ
 
 
